@@ -1,0 +1,262 @@
+/*
+ * rvpt_abi.h — the drop-in boundary of the B200 path-tracing engine.
+ *
+ * Plain C ABI (no C++/torch types): the POD structs below are byte-identical to
+ * the ones RVPT hands to Vulkan today, and the entry points are what the
+ * reference's `RVPT::update()` / `RVPT::draw()` would bind instead of the
+ * per-frame buffer uploads + `vkCmdDispatch`.
+ *
+ * Reference interfaces replaced (paths relative to the RVPT tree):
+ *   - per-frame uploads            src/rvpt/rvpt.cpp:118-126
+ *   - compute dispatch + submit    src/rvpt/rvpt.cpp:350-354, 1005-1039
+ *   - scene buffers / BVH build    src/rvpt/rvpt.cpp:84-91, 824-835
+ *   - descriptor set 0, bindings   assets/shaders/compute_pass.comp:28-58
+ *
+ * Error convention: every int-returning call returns 0 on success and a
+ * negative RVPT_B200_E* code on failure; the message is available through
+ * rvpt_b200_last_error(). Nothing here ever calls exit()/abort().
+ *
+ * Threading: one ctx = one caller thread at a time. rvpt_b200_render_frame()
+ * is asynchronous on the ctx stream; frames serialise on that stream (the
+ * temporal accumulation dependency); readbacks synchronise.
+ */
+#ifndef RVPT_ABI_H
+#define RVPT_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RVPT_API
+#else
+#define RVPT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* POD structs — kept byte-for-byte (sizes 40 / 80 / 32 / 64 / 48).          */
+/* ------------------------------------------------------------------------ */
+
+/* src/rvpt/rvpt.h:77-89 ; UBO binding 0, compute_pass.comp:28-40. */
+typedef struct rvpt_render_settings
+{
+    int32_t max_bounces;              /* default 8 */
+    int32_t aa;                       /* samples per pixel per frame, default 1 */
+    uint32_t current_frame;           /* owned by the caller (rvpt.cpp:102-111) */
+    int32_t camera_mode;              /* 0 pinhole, 1 ortho, 2 spherical */
+    int32_t top_left_render_mode;     /* integrator index, default 9 (Kajiya) */
+    int32_t top_right_render_mode;
+    int32_t bottom_left_render_mode;
+    int32_t bottom_right_render_mode;
+    float split_ratio[2];             /* default 0.5, 0.5 */
+} rvpt_render_settings;
+
+/* src/rvpt/camera.cpp:55-66 ; UBO binding 4, compute_pass.comp:44-49.
+ * matrix is column-major (matrix[4*c + r]); params = aspect, fov (radians,
+ * used as the vertical field), ortho scale, 0. */
+typedef struct rvpt_camera_data
+{
+    float matrix[16];
+    float params[4];
+} rvpt_camera_data;
+
+/* src/rvpt/bvh.h:12-18 ; SSBO binding 5 ; structs.glsl:9-14.
+ * bounds = minx,maxx,miny,maxy,minz,maxz ; leaf iff primitive_count > 0 ;
+ * children of an inner node live at first_child_or_primitive and +1. */
+typedef struct rvpt_bvh_node
+{
+    uint32_t first_child_or_primitive;
+    uint32_t primitive_count;
+    float bounds[6];
+} rvpt_bvh_node;
+
+/* src/rvpt/geometry.h:76-111 ; SSBO binding 6 ; structs.glsl:1-7.
+ * The three .w lanes carry the host-side face normal (unused by the shader),
+ * material_id[0] is the material index stored as a float. */
+typedef struct rvpt_triangle
+{
+    float vertex0[4];
+    float vertex1[4];
+    float vertex2[4];
+    float material_id[4];
+} rvpt_triangle;
+
+/* src/rvpt/material.h:9-26 ; SSBO binding 7 ; structs.glsl:22-33.
+ * albedo.w = index of refraction, data[0] = type (0 Lambert, 1 mirror,
+ * 2 dielectric). */
+typedef struct rvpt_material
+{
+    float albedo[4];
+    float emission[4];
+    float data[4];
+} rvpt_material;
+
+#define RVPT_MAX_BOUNCE_STATS 64
+
+/* Counters of the last completed frame (all `aa` passes summed). */
+typedef struct rvpt_b200_stats
+{
+    uint64_t samples;                              /* pixels x aa rendered by this ctx */
+    uint64_t segments;                             /* intersect_scene calls = sum of active[] */
+    uint64_t active[RVPT_MAX_BOUNCE_STATS];        /* rays traced at bounce b */
+    uint32_t kernel_launches;                      /* kernels launched for the frame */
+    uint32_t reserved;
+} rvpt_b200_stats;
+
+/* ------------------------------------------------------------------------ */
+/* Error codes                                                              */
+/* ------------------------------------------------------------------------ */
+#define RVPT_B200_OK 0
+#define RVPT_B200_EINVAL (-1)      /* bad argument */
+#define RVPT_B200_ECUDA (-2)       /* CUDA runtime error (see last_error) */
+#define RVPT_B200_ENOSCENE (-3)    /* render before upload_scene */
+#define RVPT_B200_EUNSUPPORTED (-4) /* valid in the reference, not built yet */
+#define RVPT_B200_ENOMEM (-5)
+
+/* ------------------------------------------------------------------------ */
+/* Context flags (rvpt_b200_create)                                          */
+/* ------------------------------------------------------------------------ */
+/* Accumulate through an 8-bit UNORM temporal image exactly like the
+ * reference (rvpt.cpp:759-766, compute_pass.comp:146-148,165): prev is
+ * loaded as k/255, the running mean is clamped and stored as round(x*255).
+ * Default (flag clear) keeps the running mean in float32. */
+#define RVPT_B200_FLAG_ACCUM_RGBA8 0x1u
+/* Cover only floor(W/16) x floor(H/16) workgroups like the reference's
+ * integer-division dispatch (rvpt.cpp:1035-1036); other pixels stay 0.
+ * Default renders every pixel. */
+#define RVPT_B200_FLAG_REFERENCE_DISPATCH 0x2u
+/* Ignore the BVH and test every triangle in upload order (legacy
+ * intersect_triangles semantics; used to cross-check BVH traversal). */
+#define RVPT_B200_FLAG_BRUTE_FORCE 0x4u
+
+typedef struct rvpt_b200_ctx rvpt_b200_ctx;
+
+/* ------------------------------------------------------------------------ */
+/* Engine lifetime — replaces RVPT::initialize()/shutdown() for the compute  */
+/* path (rvpt.cpp:57-94, 407-442).                                           */
+/* ------------------------------------------------------------------------ */
+RVPT_API int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width, uint32_t height,
+                              uint32_t flags);
+RVPT_API void rvpt_b200_destroy(rvpt_b200_ctx* ctx);
+RVPT_API const char* rvpt_b200_last_error(const rvpt_b200_ctx* ctx);
+
+/* Pixel-tile partition for multi-GPU rendering: this ctx renders the 16x16
+ * tiles with (tile_id % nranks) == rank, tile_id = ty * tiles_x + tx — the
+ * reference's workgroup footprint (compute_pass.comp:27). Must be called
+ * before the first frame; default is (0, 1). Global (x, y, W) still seed the
+ * RNG (util.glsl:35-36), so the assembled image equals the 1-GPU image. */
+RVPT_API int rvpt_b200_set_partition(rvpt_b200_ctx* ctx, int rank, int nranks);
+
+/* Launch the frame kernels on a caller-owned CUDA stream (cudaStream_t) —
+ * e.g. torch's current stream — instead of the ctx's own. */
+RVPT_API int rvpt_b200_set_stream(rvpt_b200_ctx* ctx, void* cuda_stream);
+
+/* ------------------------------------------------------------------------ */
+/* Scene upload — replaces the bvh/triangle/material buffer copies           */
+/* (rvpt.cpp:123-126) and the build in initialize() (rvpt.cpp:84-86).        */
+/* `triangles` must already be in BVH-permuted order, as the reference       */
+/* uploads `sorted_triangles`. If nodes == NULL a BVH is built internally     */
+/* (rvpt_b200_build_bvh) and the triangles are permuted by it. Host pointers  */
+/* are borrowed for the duration of the call only.                           */
+/* ------------------------------------------------------------------------ */
+RVPT_API int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
+                                    const rvpt_triangle* triangles, size_t n_triangles,
+                                    const rvpt_material* materials, size_t n_materials);
+
+/* ------------------------------------------------------------------------ */
+/* One frame — replaces the settings/camera uniform copies                   */
+/* (rvpt.cpp:118-120) + record_compute_command_buffer + submit               */
+/* (rvpt.cpp:350-354, 1005-1039). `camera` is the 80-byte block of           */
+/* Camera::get_data(). Stateless w.r.t. the frame counter: uses              */
+/* settings->current_frame as given.                                         */
+/* ------------------------------------------------------------------------ */
+RVPT_API int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* settings,
+                                    const float camera[20]);
+RVPT_API int rvpt_b200_sync(rvpt_b200_ctx* ctx);
+
+/* ------------------------------------------------------------------------ */
+/* Read-back (the reference has none: its images stay on the GPU).           */
+/* All images are raster order, row 0 first, W*H pixels. With a partition,   */
+/* pixels of tiles this rank does not own are returned as 0.                 */
+/* ------------------------------------------------------------------------ */
+/* result_image, rgba8 (binding 1): W*H*4 bytes, alpha = 0. */
+RVPT_API int rvpt_b200_read_output_rgba8(rvpt_b200_ctx* ctx, uint8_t* dst);
+/* temporal accumulation as float32 RGBA (w = 0): W*H*4 floats. In
+ * ACCUM_RGBA8 mode this is the temporal image decoded as k/255. */
+RVPT_API int rvpt_b200_read_accum_f32(rvpt_b200_ctx* ctx, float* dst);
+/* Restore the temporal accumulation (checkpoint/resume). */
+RVPT_API int rvpt_b200_write_accum_f32(rvpt_b200_ctx* ctx, const float* src);
+/* Zero the temporal accumulation and the output image. */
+RVPT_API int rvpt_b200_reset_accum(rvpt_b200_ctx* ctx);
+/* Counters of the most recent frame (synchronises). */
+RVPT_API int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out);
+
+/* ------------------------------------------------------------------------ */
+/* Device-side tile buffers, for the multi-GPU gather (NCCL runs in the      */
+/* caller: torch.distributed). Layout: [n_local_tiles_padded][256] pixels,   */
+/* local tile j = global tile j*nranks + rank, pixel order inside a tile:    */
+/* idx = warp*32 + lane, warp = (py/4)*2 + (px/8), lane = (py%4)*8 + (px%8). */
+/* n_local_tiles_padded = ceil(n_tiles / nranks) on every rank.              */
+/* ------------------------------------------------------------------------ */
+typedef struct rvpt_b200_tile_info
+{
+    uint32_t width, height;
+    uint32_t tiles_x, tiles_y;
+    uint32_t rank, nranks;
+    uint32_t n_local_tiles;        /* tiles owned by this rank */
+    uint32_t n_local_tiles_padded; /* equal on all ranks */
+    void* d_accum_tiles;           /* float4 per pixel (uchar4 in ACCUM_RGBA8 mode) */
+    void* d_rgba8_tiles;           /* uchar4 per pixel */
+    uint64_t accum_bytes;          /* of the padded buffer */
+    uint64_t rgba8_bytes;
+} rvpt_b200_tile_info;
+RVPT_API int rvpt_b200_get_tile_info(rvpt_b200_ctx* ctx, rvpt_b200_tile_info* out);
+
+/* Redirect the per-tile outputs into caller-owned device memory (e.g. this
+ * rank's slot of an all-gather buffer) so the frame kernels write the gather
+ * payload in place and no pack pass exists. Pass NULL to keep the current
+ * buffer. Sizes as reported by rvpt_b200_get_tile_info(). */
+RVPT_API int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_tiles,
+                                          void* d_rgba8_tiles);
+
+/* Scatter gathered tile buffers ([nranks][n_local_tiles_padded][256]) into a
+ * raster image on the device (the `k_untile` step on the gathering rank).
+ * elem_bytes is 4 (rgba8) or 16 (float4). Runs on the ctx stream. */
+RVPT_API int rvpt_b200_untile(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
+                              uint32_t elem_bytes, uint32_t nranks);
+
+/* ------------------------------------------------------------------------ */
+/* Host-side utilities (no GPU needed).                                      */
+/* ------------------------------------------------------------------------ */
+/* Binned-SAH BVH builder producing the reference's node format — the
+ * counterpart of BinnedBvhBuilder::build_bvh (bvh_builder.cpp:11-199) with
+ * its two defects fixed. nodes_out must hold 2*n-1 nodes,
+ * prim_indices_out n indices (the permutation: sorted[i] =
+ * triangles[prim_indices_out[i]], bvh.h:70-77). */
+RVPT_API int rvpt_b200_build_bvh(const rvpt_triangle* triangles, size_t n_triangles,
+                                 rvpt_bvh_node* nodes_out, size_t* n_nodes_out,
+                                 uint32_t* prim_indices_out);
+
+/* Camera::get_data() (camera.cpp:17-25, 55-66) without glm: translation,
+ * rotation in degrees (rotation.x about UP, .y about RIGHT, .z about FORWARD),
+ * fov in degrees. Writes the 80-byte block. */
+RVPT_API void rvpt_b200_camera_data(const float translation[3], const float rotation_deg[3],
+                                    float aspect, float fov_deg, float scale, float out[20]);
+
+/* ABI / build self-description. */
+RVPT_API uint32_t rvpt_b200_abi_version(void);
+RVPT_API const char* rvpt_b200_build_info(void);
+
+/* Evaluates the shared arithmetic header on the device for n inputs
+ * (test hook: proves device == host bit-for-bit). op: 0 sincos(x) -> (s,c),
+ * 1 rand stream from seed bits -> 2 floats, 2 normalize(x,y,z). */
+RVPT_API int rvpt_b200_selftest_math(int device, int op, const float* in, size_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RVPT_ABI_H */

@@ -1,0 +1,143 @@
+/*
+ * device_scene.h — how the scene, the path state and the frame constants are
+ * laid out in HBM / shared memory. Shared by the host-side packer (engine.cu)
+ * and the kernels (kernels.cu).
+ */
+#ifndef RVPT_DEVICE_SCENE_H
+#define RVPT_DEVICE_SCENE_H
+
+#include <stdint.h>
+
+#define RVPT_TILE_DIM 16u          /* reference workgroup footprint, compute_pass.comp:27 */
+#define RVPT_TILE_PIXELS 256u
+#define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
+#define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
+#define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
+
+/*
+ * BVH node, 32 B (two 128-bit loads). Nodes are re-laid-out in the order the
+ * reference's stack walk visits them (intersection.glsl:361-413: push
+ * first+1, descend into first), so the first child of an inner node is always
+ * node+1 and the walk needs no stack: `skip` is where the reference's
+ * `stack[--stack_ptr]` pop would land after this subtree.
+ */
+struct DevNode
+{
+    float bmin_x, bmax_x, bmin_y, bmax_y; /* bounds[0..3] */
+    float bmin_z, bmax_z;                 /* bounds[4..5] */
+    uint32_t skip;                        /* next node when this subtree is done / missed */
+    uint32_t leaf_first;                  /* first DevTri of a leaf, RVPT_NODE_INNER otherwise */
+};
+
+/*
+ * Triangle record, 4 x float4: everything intersect_triangle_fast
+ * (intersection.glsl:267-323) recomputes per ray but that only depends on the
+ * triangle, evaluated once at upload with the same unfused float32 operations:
+ *   a = v0.xyz, inv_det          inv_det = 1/(A00*A11 - A01*A10)
+ *   b = n.xyz,  A00              n = cross(e0,e1), A00 = dot(e1,e1)
+ *   c = e0.xyz, A01              A01 = A10 = -dot(e0,e1)
+ *   d = e1.xyz, A11              A11 = dot(e0,e0)
+ * Records are stored leaf by leaf in walk order; meta[i] = material index |
+ * RVPT_TRI_LAST on the last triangle of a leaf.
+ */
+struct DevTri
+{
+    float v0x, v0y, v0z, inv_det;
+    float nx, ny, nz, a00;
+    float e0x, e0y, e0z, a01;
+    float e1x, e1y, e1z, a11;
+};
+
+/* Material, 3 x float4 (convert_old_material, intersection.glsl:45-57). */
+struct DevMaterial
+{
+    float base_r, base_g, base_b, ior;       /* albedo.xyz, albedo.w */
+    float emis_r, emis_g, emis_b;            /* emission.xyz */
+    int32_t type;                            /* int(data.x) */
+    float lam_r, lam_g, lam_b, pad;          /* (base*INV_PI)*PI, integrators.glsl:622 */
+};
+
+/*
+ * The whole scene is one contiguous 16-byte-aligned blob so one TMA bulk copy
+ * (cp.async.bulk) stages it into shared memory:
+ *   [DevNode x n_nodes][DevTri x n_tris][meta u32 x n_tris (padded)][DevMaterial x n_mats]
+ */
+struct SceneLayout
+{
+    uint32_t n_nodes, n_tris, n_mats;
+    uint32_t off_tris;  /* byte offsets inside the blob */
+    uint32_t off_meta;
+    uint32_t off_mats;
+    uint32_t bytes;     /* multiple of 16 */
+    uint32_t pad;
+};
+
+/*
+ * Path state: 4 separate float4 streams (SoA), 64 B per path, indexed by queue
+ * slot so every warp moves 4 x 512 contiguous bytes.
+ *   q0 = origin.xyz,     accumulation slot (uint bits)
+ *   q1 = direction.xyz,  rng state (uint bits)
+ *   q2 = throughput.xyz, unused
+ *   q3 = radiance (col).xyz, unused
+ */
+struct PathQueue
+{
+    float4* q0;
+    float4* q1;
+    float4* q2;
+    float4* q3;
+};
+
+/* Device counters, zeroed per pass (first block) / per frame (stats). */
+struct FrameCounters
+{
+    uint32_t chunk_ctr;                 /* k_primary work distribution */
+    uint32_t pad0[3];
+    uint32_t work_ctr[64];              /* k_bounce work distribution, per bounce */
+    uint32_t qcount[64];                /* survivors pushed by bounce b (read by b+1) */
+    /* ---- not cleared between aa passes ---- */
+    unsigned long long active[64];      /* rays traced at bounce b, whole frame */
+};
+
+/* Per-frame constants, passed by value as a kernel parameter. */
+struct FrameParams
+{
+    /* image / partition */
+    uint32_t W, H;                /* full image */
+    uint32_t W_eff, H_eff;        /* rendered extent (REFERENCE_DISPATCH rounds down to 16) */
+    uint32_t tiles_x, tiles_y, n_tiles;
+    uint32_t rank, nranks;
+    uint32_t n_local_tiles;
+    uint32_t n_chunks;            /* n_local_tiles * 8 warp chunks */
+    uint32_t flags;
+    /* compute_pass.comp:50-54 */
+    float inv_dim_x, inv_dim_y;
+    uint32_t frame;
+    float frame_f;                /* float(current_frame) */
+    float inv_frame1;             /* 1/float(current_frame+1) */
+    float keep;                   /* float(min(current_frame, 1)) */
+    /* render settings */
+    int32_t max_bounces;
+    int32_t aa;
+    float aa_f;
+    int32_t pass;                 /* sample index inside the frame, 0..aa-1 */
+    int32_t camera_mode;
+    int32_t modes[4];             /* tl, tr, bl, br */
+    float split_x, split_y;
+    /* camera (camera.glsl) */
+    float cam[16];                /* column-major */
+    float aspect, hfov, scale;
+    float inv_tan_half_fov;       /* w = 1/tan(0.5*hfov), camera.glsl:44 */
+    /* buffers */
+    const unsigned char* scene;   /* blob */
+    SceneLayout layout;
+    PathQueue queue[2];
+    float4* accum_f32;            /* tile layout, float mode */
+    uchar4* accum_u8;             /* tile layout, ACCUM_RGBA8 mode */
+    uchar4* out_tiles;            /* rgba8 result, tile layout (partitioned) */
+    uchar4* out_raster;           /* rgba8 result, raster (nranks == 1) */
+    float4* carry;                /* per-slot (sum.xyz, rng) between aa passes */
+    FrameCounters* ctr;
+};
+
+#endif

@@ -1,0 +1,777 @@
+/*
+ * engine.cu — the C-ABI of include/rvpt_abi.h: context, scene packing, frame
+ * orchestration, read-backs. This is the code that sits where RVPT::update()
+ * copies its per-frame buffers (src/rvpt/rvpt.cpp:118-126) and RVPT::draw()
+ * records + submits the compute dispatch (rvpt.cpp:350-354, 1005-1039).
+ *
+ * There is no CPU fallback: every entry point that renders needs a CUDA
+ * device and fails with RVPT_B200_ECUDA otherwise.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rvpt_abi.h"
+#include "../../include/rvpt_math.h"
+#include "device_scene.h"
+#include "kernels.h"
+
+static_assert(sizeof(rvpt_render_settings) == 40, "RenderSettings must stay 40 bytes");
+static_assert(sizeof(rvpt_camera_data) == 80, "camera block must stay 80 bytes");
+static_assert(sizeof(rvpt_bvh_node) == 32, "BvhNode must stay 32 bytes");
+static_assert(sizeof(rvpt_triangle) == 64, "Triangle must stay 64 bytes");
+static_assert(sizeof(rvpt_material) == 48, "Material must stay 48 bytes");
+static_assert(sizeof(DevNode) == 32 && sizeof(DevTri) == 64 && sizeof(DevMaterial) == 48,
+              "device records are 2/4/3 float4");
+
+#define RVPT_ABI_VERSION 1u
+/* scenes whose blob fits this budget are staged into shared memory per CTA */
+#define RVPT_SMEM_SCENE_LIMIT (64u * 1024u)
+
+struct rvpt_b200_ctx
+{
+    int device = 0;
+    uint32_t W = 0, H = 0, flags = 0;
+    uint32_t tiles_x = 0, tiles_y = 0, n_tiles = 0;
+    uint32_t rank = 0, nranks = 1;
+    uint32_t n_local_tiles = 0, n_local_padded = 0;
+    int num_sms = 0;
+    int grid_primary = 0, grid_bounce = 0;
+
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+
+    /* scene */
+    unsigned char* d_scene = nullptr;
+    SceneLayout layout{};
+    bool scene_smem = false;
+    bool have_scene = false;
+
+    /* frame buffers (tile layout) */
+    void* d_accum = nullptr;      /* own allocation */
+    void* d_out_tiles = nullptr;  /* own allocation */
+    void* accum = nullptr;        /* in use (own or external) */
+    void* out_tiles = nullptr;
+    uchar4* d_out_raster = nullptr; /* nranks == 1 */
+    float4* d_carry = nullptr;      /* allocated on first aa > 1 */
+    PathQueue queue[2]{};
+    FrameCounters* d_ctr = nullptr;
+    void* d_scratch = nullptr; /* raster-sized float4 staging for read-backs */
+    bool buffers_ready = false;
+    bool frame_rendered = false;
+    int last_max_bounces = 0;
+    int last_aa = 0;
+    uint32_t last_launches = 0;
+
+    std::string err;
+};
+
+namespace
+{
+
+int fail(rvpt_b200_ctx* ctx, int code, const char* fmt, ...)
+{
+    if (ctx)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do                                                                                        \
+    {                                                                                         \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, RVPT_B200_ECUDA, "%s failed: %s (%s:%d)", #call,                 \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+    } while (0)
+
+size_t accum_elem_bytes(const rvpt_b200_ctx* ctx)
+{
+    return (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? 4u : 16u;
+}
+
+void free_frame_buffers(rvpt_b200_ctx* ctx)
+{
+    cudaFree(ctx->d_accum);
+    cudaFree(ctx->d_out_tiles);
+    cudaFree(ctx->d_out_raster);
+    cudaFree(ctx->d_carry);
+    cudaFree(ctx->d_ctr);
+    cudaFree(ctx->d_scratch);
+    for (int i = 0; i < 2; ++i)
+    {
+        cudaFree(ctx->queue[i].q0);
+        cudaFree(ctx->queue[i].q1);
+        cudaFree(ctx->queue[i].q2);
+        cudaFree(ctx->queue[i].q3);
+        ctx->queue[i] = PathQueue{};
+    }
+    ctx->d_accum = ctx->d_out_tiles = nullptr;
+    ctx->accum = ctx->out_tiles = nullptr;
+    ctx->d_out_raster = nullptr;
+    ctx->d_carry = nullptr;
+    ctx->d_ctr = nullptr;
+    ctx->d_scratch = nullptr;
+    ctx->buffers_ready = false;
+}
+
+int ensure_frame_buffers(rvpt_b200_ctx* ctx)
+{
+    if (ctx->buffers_ready) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    CU(cudaMalloc(&ctx->d_accum, slots * accum_elem_bytes(ctx)));
+    CU(cudaMalloc(&ctx->d_out_tiles, slots * 4));
+    CU(cudaMemsetAsync(ctx->d_accum, 0, slots * accum_elem_bytes(ctx), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_out_tiles, 0, slots * 4, ctx->stream));
+    if (!ctx->accum) ctx->accum = ctx->d_accum;
+    if (!ctx->out_tiles) ctx->out_tiles = ctx->d_out_tiles;
+    if (ctx->nranks == 1)
+    {
+        CU(cudaMalloc(&ctx->d_out_raster, (size_t)ctx->W * ctx->H * 4));
+        CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+    }
+    for (int i = 0; i < 2; ++i)
+    {
+        CU(cudaMalloc(&ctx->queue[i].q0, slots * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q1, slots * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q2, slots * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q3, slots * sizeof(float4)));
+    }
+    CU(cudaMalloc(&ctx->d_ctr, sizeof(FrameCounters)));
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(FrameCounters), ctx->stream));
+    ctx->buffers_ready = true;
+    return 0;
+}
+
+int ensure_scratch(rvpt_b200_ctx* ctx)
+{
+    if (ctx->d_scratch) return 0;
+    /* raster float4 + tile-layout float4 staging */
+    const size_t raster = (size_t)ctx->W * ctx->H * sizeof(float4);
+    const size_t tiles = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS * sizeof(float4);
+    CU(cudaMalloc(&ctx->d_scratch, raster + tiles));
+    return 0;
+}
+
+void recompute_partition(rvpt_b200_ctx* ctx)
+{
+    ctx->tiles_x = (ctx->W + RVPT_TILE_DIM - 1) / RVPT_TILE_DIM;
+    ctx->tiles_y = (ctx->H + RVPT_TILE_DIM - 1) / RVPT_TILE_DIM;
+    ctx->n_tiles = ctx->tiles_x * ctx->tiles_y;
+    ctx->n_local_padded = (ctx->n_tiles + ctx->nranks - 1) / ctx->nranks;
+    /* tiles g = j*nranks + rank < n_tiles */
+    ctx->n_local_tiles =
+        ctx->rank < ctx->n_tiles ? (ctx->n_tiles - ctx->rank + ctx->nranks - 1) / ctx->nranks : 0;
+}
+
+/* ---- scene packing -------------------------------------------------------- */
+
+struct PackedScene
+{
+    std::vector<DevNode> nodes;
+    std::vector<DevTri> tris;
+    std::vector<uint32_t> meta;
+    std::vector<DevMaterial> mats;
+};
+
+DevTri make_dev_tri(const rvpt_triangle& t)
+{
+    /* the per-triangle part of intersect_triangle_fast, intersection.glsl:289-307 */
+    const rv_f3 v0 = rv_make(t.vertex0[0], t.vertex0[1], t.vertex0[2]);
+    const rv_f3 v1 = rv_make(t.vertex1[0], t.vertex1[1], t.vertex1[2]);
+    const rv_f3 v2 = rv_make(t.vertex2[0], t.vertex2[1], t.vertex2[2]);
+    const rv_f3 e0 = rv_sub(v1, v0);
+    const rv_f3 e1 = rv_sub(v2, v0);
+    const rv_f3 n = rv_cross(e0, e1);
+    const float a00 = rv_dot(e1, e1);
+    const float a01 = -rv_dot(e0, e1);
+    const float a10 = -rv_dot(e0, e1);
+    const float a11 = rv_dot(e0, e0);
+    const float p0 = a00 * a11;
+    const float p1 = a01 * a10;
+    const float inv_det = 1.0f / (p0 - p1);
+    DevTri d;
+    d.v0x = v0.x, d.v0y = v0.y, d.v0z = v0.z, d.inv_det = inv_det;
+    d.nx = n.x, d.ny = n.y, d.nz = n.z, d.a00 = a00;
+    d.e0x = e0.x, d.e0y = e0.y, d.e0z = e0.z, d.a01 = a01;
+    d.e1x = e1.x, d.e1y = e1.y, d.e1z = e1.z, d.a11 = a11;
+    return d;
+}
+
+/* Re-lay the caller's BVH out in the order intersect_bvh's stack walk visits
+ * it (intersection.glsl:361-413) and resolve every pop into a skip link. */
+int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
+               const rvpt_triangle* tris, size_t n_tris, const rvpt_material* mats, size_t n_mats,
+               bool brute_force, PackedScene& out)
+{
+    for (size_t i = 0; i < n_tris; ++i)
+    {
+        const float m = tris[i].material_id[0];
+        if (!(m >= 0.0f) || (size_t)(int)m >= n_mats)
+            return fail(ctx, RVPT_B200_EINVAL, "triangle %zu: material index %g out of range [0,%zu)",
+                        i, (double)m, n_mats);
+    }
+    out.mats.resize(n_mats);
+    for (size_t i = 0; i < n_mats; ++i)
+    {
+        const rvpt_material& m = mats[i];
+        DevMaterial& d = out.mats[i];
+        d.base_r = m.albedo[0], d.base_g = m.albedo[1], d.base_b = m.albedo[2], d.ior = m.albedo[3];
+        d.emis_r = m.emission[0], d.emis_g = m.emission[1], d.emis_b = m.emission[2];
+        d.type = (int)m.data[0];
+        /* throughput *= mat_eval_Lambert_cos(base_color*INV_PI) = (base*INV_PI)*PI */
+        const float l0 = m.albedo[0] * RV_INV_PI, l1 = m.albedo[1] * RV_INV_PI,
+                    l2 = m.albedo[2] * RV_INV_PI;
+        d.lam_r = l0 * RV_PI, d.lam_g = l1 * RV_PI, d.lam_b = l2 * RV_PI, d.pad = 0.0f;
+    }
+
+    auto emit_leaf = [&](uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k)
+        {
+            out.tris.push_back(make_dev_tri(tris[first + k]));
+            uint32_t m = (uint32_t)(int)tris[first + k].material_id[0];
+            if (k + 1 == count) m |= RVPT_TRI_LAST;
+            out.meta.push_back(m);
+        }
+    };
+
+    if (brute_force || nodes == nullptr)
+    {
+        /* one leaf with unbounded extent: every triangle in upload order */
+        DevNode root;
+        const float inf = INFINITY;
+        root.bmin_x = -inf, root.bmax_x = inf, root.bmin_y = -inf, root.bmax_y = inf;
+        root.bmin_z = -inf, root.bmax_z = inf;
+        root.skip = RVPT_NODE_END;
+        root.leaf_first = 0;
+        out.nodes.push_back(root);
+        emit_leaf(0, (uint32_t)n_tris);
+        return 0;
+    }
+
+    if (n_nodes == 0) return fail(ctx, RVPT_B200_EINVAL, "BVH has no nodes");
+
+    /* Pre-order walk, first child first — exactly the order in which the
+     * shader's loop pops nodes. `pending` is the shader's stack_ptr on arrival
+     * (sentinel included); an inner node reached with 64 entries would write
+     * stack[64], which is undefined behaviour in the reference. */
+    struct Visit
+    {
+        uint32_t src;
+        uint32_t pending;
+    };
+    std::vector<Visit> todo;
+    std::vector<uint32_t> inner_of; /* per emitted node: 1 if inner */
+    todo.push_back({0u, 1u});
+    out.nodes.reserve(n_nodes);
+    size_t visited = 0;
+    while (!todo.empty())
+    {
+        const Visit f = todo.back();
+        todo.pop_back();
+        if (f.src >= n_nodes)
+            return fail(ctx, RVPT_B200_EINVAL, "BVH child index %u out of range (%zu nodes)", f.src,
+                        n_nodes);
+        if (++visited > n_nodes)
+            return fail(ctx, RVPT_B200_EINVAL, "BVH is not a tree (cycle or shared child)");
+        const rvpt_bvh_node& s = nodes[f.src];
+        DevNode d;
+        d.bmin_x = s.bounds[0], d.bmax_x = s.bounds[1], d.bmin_y = s.bounds[2];
+        d.bmax_y = s.bounds[3], d.bmin_z = s.bounds[4], d.bmax_z = s.bounds[5];
+        d.skip = RVPT_NODE_END;
+        d.leaf_first = RVPT_NODE_INNER;
+        if (s.primitive_count > 0)
+        {
+            if ((size_t)s.first_child_or_primitive + s.primitive_count > n_tris)
+                return fail(ctx, RVPT_B200_EINVAL, "BVH leaf %u: triangles [%u,%u) out of range", f.src,
+                            s.first_child_or_primitive,
+                            s.first_child_or_primitive + s.primitive_count);
+            d.leaf_first = (uint32_t)out.tris.size();
+            emit_leaf(s.first_child_or_primitive, s.primitive_count);
+            inner_of.push_back(0);
+        }
+        else
+        {
+            if (f.pending >= 64)
+                return fail(ctx, RVPT_B200_EUNSUPPORTED,
+                            "BVH needs more than the reference's 64-entry traversal stack");
+            /* second child is popped after the first child's whole subtree */
+            todo.push_back({s.first_child_or_primitive + 1, f.pending});
+            todo.push_back({s.first_child_or_primitive, f.pending + 1});
+            inner_of.push_back(1);
+        }
+        out.nodes.push_back(d);
+    }
+    /* subtree sizes in reverse pre-order; the node after a subtree is where the
+     * shader's pop lands, i.e. the skip link */
+    const uint32_t total = (uint32_t)out.nodes.size();
+    std::vector<uint32_t> size(total, 1);
+    for (uint32_t k = total; k-- > 0;)
+    {
+        if (inner_of[k])
+        {
+            const uint32_t c0 = k + 1;
+            const uint32_t c1 = c0 + size[c0];
+            size[k] = 1 + size[c0] + size[c1];
+        }
+        const uint32_t next = k + size[k];
+        out.nodes[k].skip = next < total ? next : RVPT_NODE_END;
+    }
+    return 0;
+}
+
+int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
+{
+    SceneLayout L{};
+    L.n_nodes = (uint32_t)ps.nodes.size();
+    L.n_tris = (uint32_t)ps.tris.size();
+    L.n_mats = (uint32_t)ps.mats.size();
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t off = align16(ps.nodes.size() * sizeof(DevNode));
+    L.off_tris = (uint32_t)off;
+    off = align16(off + ps.tris.size() * sizeof(DevTri));
+    L.off_meta = (uint32_t)off;
+    off = align16(off + ps.meta.size() * sizeof(uint32_t));
+    L.off_mats = (uint32_t)off;
+    off = align16(off + ps.mats.size() * sizeof(DevMaterial));
+    if (off > 0xFFFFFFF0u) return fail(ctx, RVPT_B200_EUNSUPPORTED, "scene larger than 4 GiB");
+    L.bytes = (uint32_t)off;
+
+    std::vector<unsigned char> blob(L.bytes, 0);
+    std::memcpy(blob.data(), ps.nodes.data(), ps.nodes.size() * sizeof(DevNode));
+    std::memcpy(blob.data() + L.off_tris, ps.tris.data(), ps.tris.size() * sizeof(DevTri));
+    std::memcpy(blob.data() + L.off_meta, ps.meta.data(), ps.meta.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + L.off_mats, ps.mats.data(), ps.mats.size() * sizeof(DevMaterial));
+
+    CU(cudaSetDevice(ctx->device));
+    /* frames in flight still read the old blob */
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_scene);
+    ctx->d_scene = nullptr;
+    CU(cudaMalloc(&ctx->d_scene, L.bytes));
+    CU(cudaMemcpyAsync(ctx->d_scene, blob.data(), L.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); /* blob is a stack temporary */
+    ctx->layout = L;
+    ctx->scene_smem = L.bytes <= RVPT_SMEM_SCENE_LIMIT;
+
+    int occ_p = 0, occ_b = 0;
+    if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
+    CU(rvpt::occupancy(&occ_p, &occ_b, ctx->scene_smem, L.bytes));
+    if (occ_p < 1 || occ_b < 1)
+        return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d)", occ_p,
+                    occ_b);
+    ctx->grid_primary = ctx->num_sms * occ_p;
+    ctx->grid_bounce = ctx->num_sms * occ_b;
+    ctx->have_scene = true;
+    return 0;
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+/* C ABI                                                                     */
+/* ======================================================================== */
+
+extern "C" uint32_t rvpt_b200_abi_version(void) { return RVPT_ABI_VERSION; }
+
+extern "C" const char* rvpt_b200_build_info(void)
+{
+    return "rvpt_b200 sm_100a wavefront path tracer; arithmetic: unfused fp32 (rvpt_math.h); "
+           "built " __DATE__;
+}
+
+extern "C" const char* rvpt_b200_last_error(const rvpt_b200_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width, uint32_t height,
+                                uint32_t flags)
+{
+    if (!out) return RVPT_B200_EINVAL;
+    *out = nullptr;
+    rvpt_b200_ctx* ctx = new (std::nothrow) rvpt_b200_ctx();
+    if (!ctx) return RVPT_B200_ENOMEM;
+    *out = ctx; /* returned even on failure so last_error() can be read; destroy it */
+    if (width == 0 || height == 0 || width > 65536 || height > 65536)
+        return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
+    if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
+                  RVPT_B200_FLAG_BRUTE_FORCE))
+        return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
+    ctx->device = device;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->flags = flags;
+    recompute_partition(ctx);
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ctx, RVPT_B200_ECUDA, "no CUDA device: %s (this engine has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return fail(ctx, RVPT_B200_EINVAL, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(ctx, RVPT_B200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    ctx->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    return 0;
+}
+
+extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
+{
+    if (!ctx) return;
+    if (ctx->own_stream)
+    {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        free_frame_buffers(ctx);
+        cudaFree(ctx->d_scene);
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    delete ctx;
+}
+
+extern "C" int rvpt_b200_set_partition(rvpt_b200_ctx* ctx, int rank, int nranks)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(ctx, RVPT_B200_EINVAL, "bad partition rank %d of %d", rank, nranks);
+    if (ctx->buffers_ready)
+        return fail(ctx, RVPT_B200_EINVAL, "set_partition must precede the first frame");
+    ctx->rank = (uint32_t)rank;
+    ctx->nranks = (uint32_t)nranks;
+    recompute_partition(ctx);
+    return 0;
+}
+
+extern "C" int rvpt_b200_set_stream(rvpt_b200_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes,
+                                      size_t n_nodes, const rvpt_triangle* triangles,
+                                      size_t n_triangles, const rvpt_material* materials,
+                                      size_t n_materials)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (!triangles || n_triangles == 0) return fail(ctx, RVPT_B200_EINVAL, "scene has no triangles");
+    if (!materials || n_materials == 0) return fail(ctx, RVPT_B200_EINVAL, "scene has no materials");
+    if (n_triangles > 0x7FFFFFFFu) return fail(ctx, RVPT_B200_EUNSUPPORTED, "too many triangles");
+
+    const bool brute = (ctx->flags & RVPT_B200_FLAG_BRUTE_FORCE) != 0;
+    PackedScene ps;
+    int rc;
+    if (!nodes && !brute)
+    {
+        /* build internally and permute, like RVPT::initialize() (rvpt.cpp:84-86) */
+        std::vector<rvpt_bvh_node> built(2 * n_triangles);
+        std::vector<uint32_t> perm(n_triangles);
+        size_t n_built = 0;
+        rc = rvpt_b200_build_bvh(triangles, n_triangles, built.data(), &n_built, perm.data());
+        if (rc) return fail(ctx, rc, "internal BVH build failed");
+        std::vector<rvpt_triangle> sorted(n_triangles);
+        for (size_t i = 0; i < n_triangles; ++i) sorted[i] = triangles[perm[i]];
+        rc = pack_scene(ctx, built.data(), n_built, sorted.data(), n_triangles, materials,
+                        n_materials, false, ps);
+    }
+    else
+        rc = pack_scene(ctx, nodes, n_nodes, triangles, n_triangles, materials, n_materials, brute,
+                        ps);
+    if (rc) return rc;
+    return upload_packed(ctx, ps);
+}
+
+extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs,
+                                      const float camera[20])
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (!rs || !camera) return fail(ctx, RVPT_B200_EINVAL, "null settings/camera");
+    if (!ctx->have_scene) return fail(ctx, RVPT_B200_ENOSCENE, "render_frame before upload_scene");
+    if (rs->aa < 1) return fail(ctx, RVPT_B200_EINVAL, "aa = %d (reference divides by it)", rs->aa);
+    if (rs->max_bounces < 0 || rs->max_bounces > 64)
+        return fail(ctx, RVPT_B200_EINVAL, "max_bounces = %d outside [0,64]", rs->max_bounces);
+    const int modes[4] = {rs->top_left_render_mode, rs->top_right_render_mode,
+                          rs->bottom_left_render_mode, rs->bottom_right_render_mode};
+    for (int m : modes)
+        if (m != 9)
+            return fail(ctx, RVPT_B200_EUNSUPPORTED,
+                        "render mode %d: only integrator 9 (Kajiya) is on the B200 hot path", m);
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (rs->aa > 1 && !ctx->d_carry)
+        CU(cudaMalloc(&ctx->d_carry,
+                      (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS * sizeof(float4)));
+
+    FrameParams p{};
+    p.W = ctx->W, p.H = ctx->H;
+    p.W_eff = ctx->W, p.H_eff = ctx->H;
+    if (ctx->flags & RVPT_B200_FLAG_REFERENCE_DISPATCH)
+    {
+        p.W_eff = (ctx->W / 16u) * 16u; /* rvpt.cpp:1035-1036 */
+        p.H_eff = (ctx->H / 16u) * 16u;
+    }
+    p.tiles_x = ctx->tiles_x, p.tiles_y = ctx->tiles_y, p.n_tiles = ctx->n_tiles;
+    p.rank = ctx->rank, p.nranks = ctx->nranks;
+    p.n_local_tiles = ctx->n_local_tiles;
+    p.n_chunks = ctx->n_local_tiles * 8u;
+    p.flags = ctx->flags;
+    p.inv_dim_x = 1.0f / (float)ctx->W;
+    p.inv_dim_y = 1.0f / (float)ctx->H;
+    p.frame = rs->current_frame;
+    p.frame_f = (float)rs->current_frame;
+    p.inv_frame1 = 1.0f / (float)(rs->current_frame + 1u);
+    p.keep = (float)(rs->current_frame < 1u ? rs->current_frame : 1u);
+    p.max_bounces = rs->max_bounces;
+    p.aa = rs->aa;
+    p.aa_f = (float)rs->aa;
+    p.camera_mode = rs->camera_mode;
+    for (int i = 0; i < 4; ++i) p.modes[i] = modes[i];
+    p.split_x = rs->split_ratio[0], p.split_y = rs->split_ratio[1];
+    std::memcpy(p.cam, camera, 16 * sizeof(float));
+    p.aspect = camera[16], p.hfov = camera[17], p.scale = camera[18];
+    p.inv_tan_half_fov = 1.0f / rv_tan(0.5f * p.hfov); /* camera.glsl:44 */
+    p.scene = ctx->d_scene;
+    p.layout = ctx->layout;
+    p.queue[0] = ctx->queue[0], p.queue[1] = ctx->queue[1];
+    p.accum_f32 = (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? nullptr : (float4*)ctx->accum;
+    p.accum_u8 = (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? (uchar4*)ctx->accum : nullptr;
+    p.out_tiles = (uchar4*)ctx->out_tiles;
+    p.out_raster = ctx->nranks == 1 ? ctx->d_out_raster : nullptr;
+    p.carry = ctx->d_carry;
+    p.ctr = ctx->d_ctr;
+
+    uint32_t launches = 0;
+    for (int pass = 0; pass < rs->aa; ++pass)
+    {
+        p.pass = pass;
+        const size_t clear = pass == 0 ? sizeof(FrameCounters) : offsetof(FrameCounters, active);
+        CU(cudaMemsetAsync(ctx->d_ctr, 0, clear, ctx->stream));
+        if (p.n_chunks > 0)
+        {
+            CU(rvpt::launch_primary(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
+            ++launches;
+            for (int b = 1; b < rs->max_bounces; ++b)
+            {
+                CU(rvpt::launch_bounce(p, b, ctx->scene_smem, ctx->grid_bounce, ctx->stream));
+                ++launches;
+            }
+        }
+    }
+    ctx->frame_rendered = true;
+    ctx->last_max_bounces = rs->max_bounces;
+    ctx->last_aa = rs->aa;
+    ctx->last_launches = launches;
+    return 0;
+}
+
+extern "C" int rvpt_b200_sync(rvpt_b200_ctx* ctx)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_read_output_rgba8(rvpt_b200_ctx* ctx, uint8_t* dst)
+{
+    if (!ctx || !dst) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ctx->W * ctx->H * 4;
+    if (ctx->nranks == 1)
+    {
+        CU(cudaMemcpyAsync(dst, ctx->d_out_raster, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    else
+    {
+        rc = ensure_scratch(ctx);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(ctx->d_scratch, 0, bytes, ctx->stream));
+        CU(rvpt::launch_untile(ctx->out_tiles, ctx->d_scratch, 1, ctx->W, ctx->H, ctx->tiles_x,
+                               ctx->n_tiles, ctx->nranks, ctx->rank, 1, ctx->n_local_padded,
+                               ctx->stream));
+        CU(cudaMemcpyAsync(dst, ctx->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_read_accum_f32(rvpt_b200_ctx* ctx, float* dst)
+{
+    if (!ctx || !dst) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const size_t raster_bytes = (size_t)ctx->W * ctx->H * sizeof(float4);
+    const uint64_t slots = (uint64_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    unsigned char* raster = (unsigned char*)ctx->d_scratch;
+    const void* tiles = ctx->accum;
+    if (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8)
+    {
+        void* staged = raster + raster_bytes;
+        CU(rvpt::launch_u8_to_f32(ctx->accum, staged, slots, ctx->stream));
+        tiles = staged;
+    }
+    CU(cudaMemsetAsync(raster, 0, raster_bytes, ctx->stream));
+    CU(rvpt::launch_untile(tiles, raster, 4, ctx->W, ctx->H, ctx->tiles_x, ctx->n_tiles, ctx->nranks,
+                           ctx->rank, 1, ctx->n_local_padded, ctx->stream));
+    CU(cudaMemcpyAsync(dst, raster, raster_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_write_accum_f32(rvpt_b200_ctx* ctx, const float* src)
+{
+    if (!ctx || !src) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const size_t raster_bytes = (size_t)ctx->W * ctx->H * sizeof(float4);
+    const uint64_t slots = (uint64_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    unsigned char* raster = (unsigned char*)ctx->d_scratch;
+    CU(cudaMemcpyAsync(raster, src, raster_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8)
+    {
+        void* staged = raster + raster_bytes;
+        CU(rvpt::launch_tile(raster, staged, 4, ctx->W, ctx->H, ctx->tiles_x, ctx->n_tiles,
+                             ctx->nranks, ctx->rank, ctx->n_local_padded, ctx->stream));
+        CU(rvpt::launch_f32_to_u8(staged, ctx->accum, slots, ctx->stream));
+    }
+    else
+        CU(rvpt::launch_tile(raster, ctx->accum, 4, ctx->W, ctx->H, ctx->tiles_x, ctx->n_tiles,
+                             ctx->nranks, ctx->rank, ctx->n_local_padded, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); /* src is borrowed for the call only */
+    return 0;
+}
+
+extern "C" int rvpt_b200_reset_accum(rvpt_b200_ctx* ctx)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    CU(cudaMemsetAsync(ctx->accum, 0, slots * accum_elem_bytes(ctx), ctx->stream));
+    CU(cudaMemsetAsync(ctx->out_tiles, 0, slots * 4, ctx->stream));
+    if (ctx->d_out_raster)
+        CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
+{
+    if (!ctx || !out) return RVPT_B200_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    if (!ctx->frame_rendered) return 0;
+    CU(cudaSetDevice(ctx->device));
+    FrameCounters h;
+    CU(cudaMemcpyAsync(&h, ctx->d_ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < RVPT_MAX_BOUNCE_STATS; ++b)
+    {
+        out->active[b] = h.active[b];
+        out->segments += h.active[b];
+    }
+    out->samples = ctx->last_max_bounces > 0 ? h.active[0] : 0;
+    out->kernel_launches = ctx->last_launches;
+    return 0;
+}
+
+extern "C" int rvpt_b200_get_tile_info(rvpt_b200_ctx* ctx, rvpt_b200_tile_info* out)
+{
+    if (!ctx || !out) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    out->width = ctx->W, out->height = ctx->H;
+    out->tiles_x = ctx->tiles_x, out->tiles_y = ctx->tiles_y;
+    out->rank = ctx->rank, out->nranks = ctx->nranks;
+    out->n_local_tiles = ctx->n_local_tiles;
+    out->n_local_tiles_padded = ctx->n_local_padded;
+    out->d_accum_tiles = ctx->accum;
+    out->d_rgba8_tiles = ctx->out_tiles;
+    const uint64_t slots = (uint64_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    out->accum_bytes = slots * accum_elem_bytes(ctx);
+    out->rgba8_bytes = slots * 4;
+    return 0;
+}
+
+extern "C" int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_tiles,
+                                            void* d_rgba8_tiles)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (d_accum_tiles) ctx->accum = d_accum_tiles;
+    if (d_rgba8_tiles) ctx->out_tiles = d_rgba8_tiles;
+    return 0;
+}
+
+extern "C" int rvpt_b200_untile(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
+                                uint32_t elem_bytes, uint32_t nranks)
+{
+    if (!ctx || !d_gathered || !d_raster) return RVPT_B200_EINVAL;
+    if (elem_bytes != 4 && elem_bytes != 16)
+        return fail(ctx, RVPT_B200_EINVAL, "untile element size %u (want 4 or 16)", elem_bytes);
+    if (nranks != ctx->nranks)
+        return fail(ctx, RVPT_B200_EINVAL, "untile nranks %u != partition %u", nranks, ctx->nranks);
+    CU(cudaSetDevice(ctx->device));
+    CU(rvpt::launch_untile(d_gathered, d_raster, elem_bytes / 4, ctx->W, ctx->H, ctx->tiles_x,
+                           ctx->n_tiles, ctx->nranks, 0, ctx->nranks, ctx->n_local_padded,
+                           ctx->stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_selftest_math(int device, int op, const float* in, size_t n, float* out)
+{
+    if (!in || !out || n == 0 || op < 0 || op > 3) return RVPT_B200_EINVAL;
+    static const size_t in_w[4] = {1, 1, 3, 4}, out_w[4] = {2, 2, 3, 2};
+    if (cudaSetDevice(device) != cudaSuccess) return RVPT_B200_ECUDA;
+    float *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, n * in_w[op] * 4) != cudaSuccess) return RVPT_B200_ECUDA;
+    if (cudaMalloc(&d_out, n * out_w[op] * 4) != cudaSuccess)
+    {
+        cudaFree(d_in);
+        return RVPT_B200_ECUDA;
+    }
+    int rc = 0;
+    if (cudaMemcpy(d_in, in, n * in_w[op] * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        rvpt::launch_selftest(op, d_in, n, d_out, 0) != cudaSuccess ||
+        cudaMemcpy(out, d_out, n * out_w[op] * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = RVPT_B200_ECUDA;
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}

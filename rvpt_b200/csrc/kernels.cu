@@ -1,0 +1,812 @@
+/*
+ * kernels.cu — the sm_100a wavefront path-tracing kernels.
+ *
+ * Replaces the reference's per-pixel megakernel (assets/shaders/compute_pass.comp
+ * ::main and everything it includes) with
+ *
+ *   k_primary   ray generation + bounce 0, fused (camera.glsl:29-99,
+ *               compute_pass.comp:121-167, integrators.glsl:547-677 iteration 0)
+ *   k_bounce    one launch per later bounce over the compacted path queue
+ *               (integrators.glsl:574-671 iteration b)
+ *
+ * Paths that terminate do the temporal accumulation in place
+ * (compute_pass.comp:146-148,161-166); survivors are compacted with a warp
+ * ballot into the next SoA queue. The scene (BVH nodes, precomputed triangle
+ * records, materials) is staged per CTA into shared memory with one TMA bulk
+ * copy; CTAs are persistent and pull work with an atomic counter.
+ *
+ * Arithmetic follows include/rvpt_math.h (unfused float32, -fmad=false) so the
+ * result is bit-identical to oracle/rvpt_oracle.cpp.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rvpt_abi.h"
+#include "../../include/rvpt_math.h"
+#include "device_scene.h"
+#include "kernels.h"
+
+namespace
+{
+
+constexpr int kThreads = 256;      /* one reference workgroup worth of pixels */
+constexpr int kWarpsPerCta = kThreads / 32;
+constexpr uint32_t kChunkGrain = 4; /* 32-pixel chunks a warp claims per atomic */
+constexpr uint32_t kRayGrain = 4;   /* 32-ray groups a warp claims per atomic */
+
+#define RV_INF __int_as_float(0x7f800000)
+
+/* ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    uint32_t done = 0;
+    while (!done)
+    {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+
+/* Stage the scene blob into shared memory: one elected thread arms the
+ * mbarrier with the byte count and issues the bulk copies (<= 32 KB each);
+ * everybody waits on the barrier phase. */
+__device__ __forceinline__ void stage_scene(unsigned char* smem_blob, uint64_t* bar,
+                                            const unsigned char* gmem_blob, uint32_t bytes)
+{
+    if (threadIdx.x == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+        {
+            uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+            tma_bulk_g2s(smem_blob + off, gmem_blob + off, n, bar);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+}
+
+/* ---- scene view ---------------------------------------------------------- */
+
+struct SceneView
+{
+    const float4* nodes; /* 2 per node */
+    const float4* tris;  /* 4 per triangle */
+    const uint32_t* meta;
+    const float4* mats;  /* 3 per material */
+};
+
+__device__ __forceinline__ SceneView make_view(const unsigned char* base, const SceneLayout& L)
+{
+    SceneView v;
+    v.nodes = reinterpret_cast<const float4*>(base);
+    v.tris = reinterpret_cast<const float4*>(base + L.off_tris);
+    v.meta = reinterpret_cast<const uint32_t*>(base + L.off_meta);
+    v.mats = reinterpret_cast<const float4*>(base + L.off_mats);
+    return v;
+}
+
+/* ---- nearest hit: stackless walk in the reference's visiting order ------- */
+
+__device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f3 d, float& best_t,
+                                              uint32_t& best_tri)
+{
+    /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    best_t = RV_INF;
+    best_tri = 0xFFFFFFFFu;
+    uint32_t node = 0;
+    while (node != RVPT_NODE_END)
+    {
+        const float4 n0 = sc.nodes[2 * node];
+        const float4 n1 = sc.nodes[2 * node + 1];
+        const float fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
+        const float fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
+        const float fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
+        float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+        float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+        t0 = fmaxf(t0, 0.0f);
+        t1 = fminf(t1, best_t);
+        const uint32_t skip = __float_as_uint(n1.z);
+        const uint32_t leaf = __float_as_uint(n1.w);
+        if (t1 >= t0)
+        {
+            if (leaf != RVPT_NODE_INNER)
+            {
+                uint32_t i = leaf;
+                uint32_t m;
+                do
+                {
+                    /* intersect_triangle_fast (intersection.glsl:267-323) on the
+                     * precomputed record; the early-out is value-neutral because
+                     * the acceptance test is a pure conjunction. */
+                    const float4 A = sc.tris[4 * i + 0];
+                    const float4 B = sc.tris[4 * i + 1];
+                    m = sc.meta[i];
+                    const float num = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
+                                             rv_make(B.x, B.y, B.z));
+                    const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
+                    const float t = num / den;
+                    if (0.0f < t && t < best_t)
+                    {
+                        const float4 C = sc.tris[4 * i + 2];
+                        const float4 D = sc.tris[4 * i + 3];
+                        const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
+                        const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
+                        const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
+                        const float by = rv_dot(p0, rv_make(D.x, D.y, D.z));
+                        const float m0 = B.w * bx, m1 = C.w * by; /* A00*bx + A10*by */
+                        const float m2 = C.w * bx, m3 = D.w * by; /* A01*bx + A11*by */
+                        const float u = A.w * (m0 + m1);
+                        const float v = A.w * (m2 + m3);
+                        if (0.0f < u && 0.0f < v && u + v < 1.0f)
+                        {
+                            best_t = t;
+                            best_tri = i;
+                        }
+                    }
+                    ++i;
+                } while (!(m & RVPT_TRI_LAST));
+                node = skip;
+            }
+            else
+                node = node + 1;
+        }
+        else
+            node = skip;
+    }
+}
+
+/* ---- slot <-> pixel ------------------------------------------------------- */
+
+__device__ __forceinline__ void slot_to_xy(const FrameParams& p, uint32_t slot, uint32_t& x,
+                                           uint32_t& y)
+{
+    const uint32_t local_tile = slot >> 8;
+    const uint32_t g = local_tile * p.nranks + p.rank;
+    const uint32_t ty = g / p.tiles_x;
+    const uint32_t tx = g - ty * p.tiles_x;
+    const uint32_t w = (slot >> 5) & 7u, lane = slot & 31u;
+    x = tx * RVPT_TILE_DIM + ((w & 1u) << 3) + (lane & 7u);
+    y = ty * RVPT_TILE_DIM + ((w >> 1) << 2) + (lane >> 3);
+}
+
+/* ---- sample termination: compute_pass.comp:146-148, 157-166 --------------- */
+
+__device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slot, rv_f3 s,
+                                              uint32_t rng)
+{
+    /* sampled = vec3(0); sampled += eval_integrator(...) */
+    rv_f3 sum;
+    if (p.pass == 0)
+        sum = rv_make(0.0f + s.x, 0.0f + s.y, 0.0f + s.z);
+    else
+    {
+        const float4 c = p.carry[slot];
+        sum = rv_make(c.x + s.x, c.y + s.y, c.z + s.z);
+    }
+    if (p.pass != p.aa - 1)
+    {
+        p.carry[slot] = make_float4(sum.x, sum.y, sum.z, __uint_as_float(rng));
+        return;
+    }
+    const rv_f3 sampled = rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f);
+
+    rv_f3 prev;
+    const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
+    if (u8)
+    {
+        const uchar4 k = p.accum_u8[slot];
+        prev = rv_make(rv_unorm8_load(k.x), rv_unorm8_load(k.y), rv_unorm8_load(k.z));
+    }
+    else
+    {
+        const float4 a = p.accum_f32[slot];
+        prev = rv_make(a.x, a.y, a.z);
+    }
+    const rv_f3 temporal = rv_make(prev.x * p.keep, prev.y * p.keep, prev.z * p.keep);
+    const rv_f3 acc = rv_make((temporal.x * p.frame_f + sampled.x) * p.inv_frame1,
+                              (temporal.y * p.frame_f + sampled.y) * p.inv_frame1,
+                              (temporal.z * p.frame_f + sampled.z) * p.inv_frame1);
+    const uchar4 q = make_uchar4((unsigned char)rv_unorm8_store(acc.x),
+                                 (unsigned char)rv_unorm8_store(acc.y),
+                                 (unsigned char)rv_unorm8_store(acc.z), 0);
+    if (u8)
+        p.accum_u8[slot] = q;
+    else
+        p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+    if (p.out_raster)
+    {
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        p.out_raster[(size_t)y * p.W + x] = q;
+    }
+    else
+        p.out_tiles[slot] = q;
+}
+
+/* ---- one iteration of integrator_Kajiya's loop (integrators.glsl:574-671) -- */
+
+struct PathState
+{
+    rv_f3 o, d, thr, col;
+    uint32_t rng;
+};
+
+/* Returns true if the path continues (state updated), false if it ended with
+ * `sample`. */
+__device__ __forceinline__ bool kajiya_step(const SceneView& sc, PathState& s, rv_f3& sample)
+{
+    float t;
+    uint32_t tri;
+    trace_nearest(sc, s.o, s.d, t, tri);
+
+    if (tri == 0xFFFFFFFFu)
+    {
+        /* :578-579 background */
+        const float k = s.d.y * 0.5f + 0.5f;
+        const rv_f3 bg = rv_make(rv_mix(1.0f, 0.2f, k), rv_mix(1.0f, 0.3f, k), rv_mix(1.0f, 0.7f, k));
+        sample = rv_add(s.col, rv_mul(s.thr, bg));
+        return false;
+    }
+
+    const float4 B = sc.tris[4 * tri + 1];
+    const uint32_t mi = sc.meta[tri] & ~RVPT_TRI_LAST;
+    const float4 M0 = sc.mats[3 * mi + 0];
+    const float4 M1 = sc.mats[3 * mi + 1];
+    const int type = __float_as_int(M1.w);
+
+    /* intersect_scene (intersection.glsl:511-513) */
+    rv_f3 normal = rv_normalize(rv_make(B.x, B.y, B.z));
+    const rv_f3 pos = rv_add(s.o, rv_scale(t, s.d));
+
+    /* :582 */
+    s.col = rv_add(s.col, rv_mul(s.thr, rv_make(M1.x, M1.y, M1.z)));
+
+    const rv_f3 dir_in = rv_normalize(s.d);
+    const float cos_view = rv_dot(dir_in, normal);
+    float cos_in;
+    float eta = M0.w;
+    if (cos_view > 0.0f)
+    {
+        cos_in = cos_view;
+        normal = rv_neg(normal);
+    }
+    else
+    {
+        cos_in = -cos_view;
+        eta = 1.0f / eta;
+    }
+
+    if (type == 0)
+    {
+        /* Lambert :617-623, material.glsl:96-108, samples_mapping.glsl:39-60,112-131 */
+        const float4 M2 = sc.mats[3 * mi + 2];
+        const float u = rv_rand(&s.rng);
+        const float v = rv_rand(&s.rng);
+        const float phi = RV_TWO_PI * u;
+        const float cos_theta = (1.0f - v) - v;
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        float sn, cs;
+        rv_sincos(phi, &sn, &cs);
+        s.o = rv_add(pos, rv_scale(RV_EPSILON, normal));
+        s.d = rv_add(normal, rv_make(sin_theta * cs, sin_theta * sn, cos_theta));
+        s.thr = rv_mul(s.thr, rv_make(M2.x, M2.y, M2.z));
+        return true;
+    }
+    if (type == 1)
+    {
+        /* mirror :625-631 */
+        s.o = rv_add(pos, rv_scale(RV_EPSILON, normal));
+        s.d = rv_add(dir_in, rv_scale(cos_in + cos_in, normal));
+        s.thr = rv_mul(s.thr, rv_make(M0.x, M0.y, M0.z));
+        return true;
+    }
+    if (type == 2)
+    {
+        /* dielectric :633-665, material.glsl:207-228 */
+        const float cos_out_sqr = 1.0f - (eta * eta) * (1.0f - cos_in * cos_in);
+        float cos_out = 0.0f;
+        bool refl = (cos_out_sqr <= 0.0f);
+        if (!refl)
+        {
+            cos_out = sqrtf(fmaxf(0.0f, cos_out_sqr));
+            const float ec = eta * cos_in;
+            const float eo = eta * cos_out;
+            const float r_perp = (ec - cos_out) / (ec + cos_out);
+            const float r_par = (cos_in - eo) / (cos_in + eo);
+            const float f_refl = 0.5f * (r_perp * r_perp + r_par * r_par);
+            refl = (rv_rand(&s.rng) < f_refl);
+        }
+        if (refl)
+        {
+            s.o = rv_add(pos, rv_scale(RV_EPSILON, normal));
+            s.d = rv_add(dir_in, rv_scale(cos_in + cos_in, normal));
+        }
+        else
+        {
+            s.o = rv_sub(pos, rv_scale(RV_EPSILON, normal));
+            s.d = rv_add(rv_scale(eta, dir_in), rv_scale(eta * cos_in - cos_out, normal));
+        }
+        s.thr = rv_mul(s.thr, rv_make(M0.x, M0.y, M0.z));
+        return true;
+    }
+    /* default :666-667 */
+    sample = rv_make(0.0f, 0.0f, 0.0f);
+    return false;
+}
+
+/* Warp-aggregated append of the surviving lanes to a queue. */
+__device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQueue& q,
+                                               uint32_t* qcount, bool alive, uint32_t slot,
+                                               const PathState& s)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
+    if (mask == 0) return;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(qcount, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+    if (alive)
+    {
+        const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
+        q.q0[i] = make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot));
+        q.q1[i] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.rng));
+        q.q2[i] = make_float4(s.thr.x, s.thr.y, s.thr.z, 0.0f);
+        q.q3[i] = make_float4(s.col.x, s.col.y, s.col.z, 0.0f);
+    }
+    (void)p;
+}
+
+/* mat4 * vec4(x,y,z,w).xyz with the columns summed left to right. */
+__device__ __forceinline__ rv_f3 cam_mul(const float* M, float x, float y, float z, float w)
+{
+    float r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        const float a = M[0 + i] * x;
+        const float b = M[4 + i] * y;
+        const float c = M[8 + i] * z;
+        const float e = M[12 + i] * w;
+        float sacc = a + b;
+        sacc = sacc + c;
+        sacc = sacc + e;
+        r[i] = sacc;
+    }
+    return rv_make(r[0], r[1], r[2]);
+}
+
+/* get_camera_ray (compute_pass.comp:102-118, camera.glsl:29-99) */
+__device__ __forceinline__ void camera_ray(const FrameParams& p, float cx, float cy, rv_f3& o,
+                                           rv_f3& d)
+{
+    if (p.camera_mode == 0)
+    {
+        const float u = p.aspect * ((cx + cx) - 1.0f);
+        const float v = (cy + cy) - 1.0f;
+        o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
+        d = rv_normalize(cam_mul(p.cam, u, v, p.inv_tan_half_fov, 0.0f));
+    }
+    else if (p.camera_mode == 1)
+    {
+        const float u = p.aspect * ((cx + cx) - 1.0f);
+        const float v = (cy + cy) - 1.0f;
+        o = cam_mul(p.cam, p.scale * u, p.scale * v, 0.0f, 1.0f);
+        d = rv_make(p.cam[8], p.cam[9], p.cam[10]);
+    }
+    else
+    {
+        const float phi = cx * RV_TWO_PI;
+        const float theta = cy * RV_PI;
+        float sp, cp, st, ct;
+        rv_sincos(phi, &sp, &cp);
+        rv_sincos(theta, &st, &ct);
+        o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
+        d = cam_mul(p.cam, st * cp, ct, st * sp, 0.0f);
+    }
+}
+
+/* ======================================================================== */
+/* k_primary: generation + bounce 0                                          */
+/* ======================================================================== */
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    SceneView sc;
+    if (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view(smem, p.layout);
+    }
+    else
+        sc = make_view(p.scene, p.layout);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long traced = 0;
+
+    for (;;)
+    {
+        uint32_t c0 = 0;
+        if (lane == 0) c0 = atomicAdd(&p.ctr->chunk_ctr, kChunkGrain);
+        c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+        if (c0 >= p.n_chunks) break;
+        const uint32_t c1 = min(c0 + kChunkGrain, p.n_chunks);
+        for (uint32_t c = c0; c < c1; ++c)
+        {
+            const uint32_t slot = c * 32u + lane;
+            uint32_t x, y;
+            slot_to_xy(p, slot, x, y);
+            const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
+                                ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
+            bool alive = false;
+            PathState s;
+            if (inside)
+            {
+                /* util.glsl:35-36; later samples of the frame continue the stream */
+                if (p.pass == 0)
+                    s.rng = rv_wang_hash(x + y * p.W) + p.frame;
+                else
+                    s.rng = __float_as_uint(p.carry[slot].w);
+
+                /* compute_pass.comp:153-154 */
+                const float jx = rv_rand(&s.rng);
+                const float jy = rv_rand(&s.rng);
+                const float cx = ((float)x + jx) * p.inv_dim_x;
+                float cy = ((float)y + jy) * p.inv_dim_y;
+                cy = 1.0f - cy;
+                camera_ray(p, cx, cy, s.o, s.d);
+                s.thr = rv_make(1.0f, 1.0f, 1.0f);
+                s.col = rv_make(0.0f, 0.0f, 0.0f);
+
+                rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
+                if (p.max_bounces > 0)
+                {
+                    alive = kajiya_step(sc, s, sample);
+                    if (alive && p.max_bounces == 1)
+                    {
+                        alive = false; /* :674-675 ran out of iterations */
+                        sample = rv_make(0.0f, 0.0f, 0.0f);
+                    }
+                }
+                if (!alive) finish_sample(p, slot, sample, s.rng);
+            }
+            if (p.max_bounces > 0)
+                traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
+            push_survivors(p, p.queue[0], &p.ctr->qcount[0], alive, slot, s);
+        }
+    }
+    if (lane == 0 && traced) atomicAdd(&p.ctr->active[0], traced);
+}
+
+/* ======================================================================== */
+/* k_bounce: iteration b >= 1 over queue[(b-1)&1] -> queue[b&1]              */
+/* ======================================================================== */
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const int b)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t first_claim;
+
+    const uint32_t count = p.ctr->qcount[b - 1];
+    /* an empty wave costs one atomic per CTA and no scene staging */
+    if (threadIdx.x == 0)
+        first_claim = count ? atomicAdd(&p.ctr->work_ctr[b], 32u * kRayGrain * kWarpsPerCta) : count;
+    __syncthreads();
+    const uint32_t cta_first = first_claim;
+    if (cta_first >= count) return;
+    /* exactly one CTA claims offset 0: it records the wave size */
+    if (threadIdx.x == 0 && cta_first == 0 && b < RVPT_MAX_BOUNCE_STATS)
+        atomicAdd(&p.ctr->active[b], (unsigned long long)count);
+
+    SceneView sc;
+    if (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view(smem, p.layout);
+    }
+    else
+        sc = make_view(p.scene, p.layout);
+
+    const PathQueue qin = p.queue[(b - 1) & 1];
+    const PathQueue qout = p.queue[b & 1];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const bool last_bounce = (b == p.max_bounces - 1);
+
+    /* the CTA-level claim is split evenly between its warps; later claims are per warp */
+    uint32_t r0 = cta_first + warp * 32u * kRayGrain;
+    for (;;)
+    {
+        if (r0 >= count) break;
+        const uint32_t r1 = min(r0 + 32u * kRayGrain, count);
+        for (uint32_t base = r0; base < r1; base += 32u)
+        {
+            const uint32_t i = base + lane;
+            bool alive = false;
+            PathState s;
+            uint32_t slot = 0;
+            if (i < count)
+            {
+                const float4 a0 = qin.q0[i];
+                const float4 a1 = qin.q1[i];
+                const float4 a2 = qin.q2[i];
+                const float4 a3 = qin.q3[i];
+                s.o = rv_make(a0.x, a0.y, a0.z);
+                slot = __float_as_uint(a0.w);
+                s.d = rv_make(a1.x, a1.y, a1.z);
+                s.rng = __float_as_uint(a1.w);
+                s.thr = rv_make(a2.x, a2.y, a2.z);
+                s.col = rv_make(a3.x, a3.y, a3.z);
+
+                rv_f3 sample;
+                alive = kajiya_step(sc, s, sample);
+                if (alive && last_bounce)
+                {
+                    alive = false; /* integrators.glsl:674-675: col is discarded */
+                    sample = rv_make(0.0f, 0.0f, 0.0f);
+                }
+                if (!alive) finish_sample(p, slot, sample, s.rng);
+            }
+            push_survivors(p, qout, &p.ctr->qcount[b], alive, slot, s);
+        }
+        uint32_t nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&p.ctr->work_ctr[b], 32u * kRayGrain);
+        r0 = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+    }
+}
+
+/* ======================================================================== */
+/* tile <-> raster                                                           */
+/* ======================================================================== */
+/* src: [n_src_ranks][n_local_padded][256] elements of `words` 32-bit words;
+ * element (r, j, q) is pixel q of global tile j*nranks + first_rank + r. */
+__global__ void k_untile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                         uint32_t words, uint32_t W, uint32_t H, uint32_t tiles_x, uint32_t n_tiles,
+                         uint32_t nranks, uint32_t first_rank, uint32_t n_src_ranks,
+                         uint32_t n_local_padded)
+{
+    const uint64_t total = (uint64_t)n_src_ranks * n_local_padded * RVPT_TILE_PIXELS;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uint32_t q = (uint32_t)(e & 255u);
+        const uint64_t tj = e >> 8;
+        const uint32_t j = (uint32_t)(tj % n_local_padded);
+        const uint32_t r = (uint32_t)(tj / n_local_padded);
+        const uint32_t g = j * nranks + first_rank + r;
+        if (g >= n_tiles) continue;
+        const uint32_t ty = g / tiles_x, tx = g - ty * tiles_x;
+        const uint32_t w = q >> 5, lane = q & 31u;
+        const uint32_t x = tx * RVPT_TILE_DIM + ((w & 1u) << 3) + (lane & 7u);
+        const uint32_t y = ty * RVPT_TILE_DIM + ((w >> 1) << 2) + (lane >> 3);
+        if (x >= W || y >= H) continue;
+        const uint64_t d = ((uint64_t)y * W + x) * words;
+        if (words == 4)
+            reinterpret_cast<uint4*>(dst)[d >> 2] = reinterpret_cast<const uint4*>(src)[e];
+        else
+            for (uint32_t k = 0; k < words; ++k) dst[d + k] = src[e * words + k];
+    }
+}
+
+/* inverse of k_untile for one rank's local tiles (checkpoint restore) */
+__global__ void k_tile(const uint32_t* __restrict__ raster, uint32_t* __restrict__ tiles,
+                       uint32_t words, uint32_t W, uint32_t H, uint32_t tiles_x, uint32_t n_tiles,
+                       uint32_t nranks, uint32_t rank, uint32_t n_local_padded)
+{
+    const uint64_t total = (uint64_t)n_local_padded * RVPT_TILE_PIXELS;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uint32_t q = (uint32_t)(e & 255u);
+        const uint32_t j = (uint32_t)(e >> 8);
+        const uint32_t g = j * nranks + rank;
+        uint32_t x = 0, y = 0;
+        bool ok = g < n_tiles;
+        if (ok)
+        {
+            const uint32_t ty = g / tiles_x, tx = g - ty * tiles_x;
+            const uint32_t w = q >> 5, lane = q & 31u;
+            x = tx * RVPT_TILE_DIM + ((w & 1u) << 3) + (lane & 7u);
+            y = ty * RVPT_TILE_DIM + ((w >> 1) << 2) + (lane >> 3);
+            ok = x < W && y < H;
+        }
+        for (uint32_t k = 0; k < words; ++k)
+            tiles[e * words + k] = ok ? raster[((uint64_t)y * W + x) * words + k] : 0u;
+    }
+}
+
+/* rgba8 temporal image -> float4 (k/255) for read_accum in ACCUM_RGBA8 mode */
+__global__ void k_u8_to_f32(const uchar4* __restrict__ src, float4* __restrict__ dst, uint64_t n)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uchar4 k = src[e];
+        dst[e] = make_float4(rv_unorm8_load(k.x), rv_unorm8_load(k.y), rv_unorm8_load(k.z), 0.0f);
+    }
+}
+__global__ void k_f32_to_u8(const float4* __restrict__ src, uchar4* __restrict__ dst, uint64_t n)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const float4 a = src[e];
+        dst[e] = make_uchar4((unsigned char)rv_unorm8_store(a.x), (unsigned char)rv_unorm8_store(a.y),
+                             (unsigned char)rv_unorm8_store(a.z), 0);
+    }
+}
+
+/* ---- shared-header self test ---------------------------------------------- */
+__global__ void k_selftest(int op, const float* __restrict__ in, size_t n, float* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 0)
+    {
+        float s, c;
+        rv_sincos(in[i], &s, &c);
+        out[2 * i] = s;
+        out[2 * i + 1] = c;
+    }
+    else if (op == 1)
+    {
+        uint32_t st = __float_as_uint(in[i]);
+        out[2 * i] = rv_rand(&st);
+        out[2 * i + 1] = rv_rand(&st);
+    }
+    else if (op == 2)
+    {
+        const rv_f3 r = rv_normalize(rv_make(in[3 * i], in[3 * i + 1], in[3 * i + 2]));
+        out[3 * i] = r.x;
+        out[3 * i + 1] = r.y;
+        out[3 * i + 2] = r.z;
+    }
+    else if (op == 3)
+    {
+        /* contraction probe + tan: in = (a, b, c, x) */
+        out[2 * i] = (float)rv_contract_probe(in[4 * i], in[4 * i + 1], in[4 * i + 2]);
+        out[2 * i + 1] = 1.0f / rv_tan(0.5f * in[4 * i + 3]);
+    }
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+/* launch wrappers (called from engine.cu)                                   */
+/* ======================================================================== */
+namespace rvpt
+{
+
+static size_t smem_bytes_for(const FrameParams& p, bool smem) { return smem ? p.layout.bytes : 0; }
+
+cudaError_t configure_kernels(size_t max_dynamic_smem)
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)max_dynamic_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)max_dynamic_smem);
+    return e;
+}
+
+cudaError_t occupancy(int* primary_ctas_per_sm, int* bounce_ctas_per_sm, bool smem,
+                      size_t scene_bytes)
+{
+    const size_t dyn = smem ? scene_bytes : 0;
+    cudaError_t e;
+    if (smem)
+    {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<true>,
+                                                          kThreads, dyn);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bounce_ctas_per_sm, k_bounce<true>,
+                                                          kThreads, dyn);
+    }
+    else
+    {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<false>,
+                                                          kThreads, dyn);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bounce_ctas_per_sm, k_bounce<false>,
+                                                          kThreads, dyn);
+    }
+    return e;
+}
+
+cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)
+{
+    if (smem)
+        k_primary<true><<<grid, kThreads, smem_bytes_for(p, true), st>>>(p);
+    else
+        k_primary<false><<<grid, kThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bounce(const FrameParams& p, int b, bool smem, int grid, cudaStream_t st)
+{
+    if (smem)
+        k_bounce<true><<<grid, kThreads, smem_bytes_for(p, true), st>>>(p, b);
+    else
+        k_bounce<false><<<grid, kThreads, 0, st>>>(p, b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_untile(const void* src, void* dst, uint32_t words, uint32_t W, uint32_t H,
+                          uint32_t tiles_x, uint32_t n_tiles, uint32_t nranks, uint32_t first_rank,
+                          uint32_t n_src_ranks, uint32_t n_local_padded, cudaStream_t st)
+{
+    k_untile<<<592, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, words, W, H, tiles_x, n_tiles,
+                                  nranks, first_rank, n_src_ranks, n_local_padded);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile(const void* raster, void* tiles, uint32_t words, uint32_t W, uint32_t H,
+                        uint32_t tiles_x, uint32_t n_tiles, uint32_t nranks, uint32_t rank,
+                        uint32_t n_local_padded, cudaStream_t st)
+{
+    k_tile<<<592, 256, 0, st>>>((const uint32_t*)raster, (uint32_t*)tiles, words, W, H, tiles_x,
+                                n_tiles, nranks, rank, n_local_padded);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_u8_to_f32(const void* src, void* dst, uint64_t n, cudaStream_t st)
+{
+    k_u8_to_f32<<<592, 256, 0, st>>>((const uchar4*)src, (float4*)dst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_f32_to_u8(const void* src, void* dst, uint64_t n, cudaStream_t st)
+{
+    k_f32_to_u8<<<592, 256, 0, st>>>((const float4*)src, (uchar4*)dst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest(int op, const float* in, size_t n, float* out, cudaStream_t st)
+{
+    k_selftest<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, in, n, out);
+    return cudaGetLastError();
+}
+
+int threads_per_cta() { return kThreads; }
+
+} /* namespace rvpt */

@@ -1,0 +1,176 @@
+"""Python host mirror of the reference's renderer facade for the compute path.
+
+`Engine` plays the role `class RVPT` plays for the Vulkan path
+(src/rvpt/rvpt.h:27-90): scene in, `update()`/`draw()`-style frames out — but
+every frame goes through the C ABI of include/rvpt_abi.h into the sm_100a
+kernels. Nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .scene import BVH_NODE_DTYPE, MATERIAL_DTYPE, RENDER_SETTINGS_DTYPE, TRIANGLE_DTYPE, Scene
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rvpt_b200 error {code}: {message}")
+        self.code = code
+
+
+def build_bvh(triangles: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """BinnedBvhBuilder::build_bvh counterpart (host only). Returns
+    (nodes BVH_NODE_DTYPE[], primitive_indices uint32[]); upload
+    `triangles[primitive_indices]` like `permute_primitives` (bvh.h:70-77)."""
+    lib = _lib.load()
+    tris = np.ascontiguousarray(triangles, TRIANGLE_DTYPE)
+    n = len(tris)
+    nodes = np.zeros(max(2 * n, 1), BVH_NODE_DTYPE)
+    perm = np.zeros(n, np.uint32)
+    n_nodes = C.c_size_t(0)
+    rc = lib.rvpt_b200_build_bvh(tris.ctypes.data, n, nodes.ctypes.data, C.byref(n_nodes),
+                                 perm.ctypes.data)
+    if rc:
+        raise EngineError(rc, "build_bvh failed")
+    return nodes[: n_nodes.value].copy(), perm
+
+
+def camera_data(translation=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0), aspect: float = 2.0,
+                fov: float = 90.0, scale: float = 4.0) -> np.ndarray:
+    """Camera::get_data() (camera.cpp:55-66): 20 floats. Defaults are the
+    reference's (camera.h:44-49; aspect = window width / height)."""
+    lib = _lib.load()
+    t = np.asarray(translation, np.float32)
+    r = np.asarray(rotation, np.float32)
+    out = np.zeros(20, np.float32)
+    lib.rvpt_b200_camera_data(t.ctypes.data, r.ctypes.data, float(aspect), float(fov), float(scale),
+                              out.ctypes.data)
+    return out
+
+
+class Engine:
+    """One rendering context on one GPU (one process per GPU)."""
+
+    def __init__(self, width: int, height: int, device: int = 0, flags: int = 0,
+                 rank: int = 0, nranks: int = 1):
+        self._lib = _lib.load()
+        self.width, self.height = int(width), int(height)
+        self.flags = flags
+        self._ctx = C.c_void_p()
+        rc = self._lib.rvpt_b200_create(C.byref(self._ctx), device, width, height, flags)
+        if rc:
+            msg = self._lib.rvpt_b200_last_error(self._ctx).decode() if self._ctx else "create failed"
+            self._lib.rvpt_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            raise EngineError(rc, msg)
+        if nranks != 1:
+            self._check(self._lib.rvpt_b200_set_partition(self._ctx, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise EngineError(rc, self._lib.rvpt_b200_last_error(self._ctx).decode())
+
+    def close(self) -> None:
+        if self._ctx:
+            self._lib.rvpt_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- scene ------------------------------------------------------------
+    def upload_scene(self, triangles: np.ndarray, materials: np.ndarray,
+                     nodes: np.ndarray | None = None) -> None:
+        """rvpt.cpp:123-126. `triangles` in BVH-permuted order when `nodes`
+        is given; `nodes=None` builds the BVH inside the library."""
+        tris = np.ascontiguousarray(triangles, TRIANGLE_DTYPE)
+        mats = np.ascontiguousarray(materials, MATERIAL_DTYPE)
+        if nodes is None:
+            self._check(self._lib.rvpt_b200_upload_scene(self._ctx, None, 0, tris.ctypes.data,
+                                                         len(tris), mats.ctypes.data, len(mats)))
+        else:
+            nd = np.ascontiguousarray(nodes, BVH_NODE_DTYPE)
+            self._check(self._lib.rvpt_b200_upload_scene(self._ctx, nd.ctypes.data, len(nd),
+                                                         tris.ctypes.data, len(tris),
+                                                         mats.ctypes.data, len(mats)))
+
+    def upload(self, scene: Scene) -> tuple[np.ndarray, np.ndarray]:
+        """Builds the BVH on the host, permutes and uploads — what
+        RVPT::initialize() does (rvpt.cpp:84-86). Returns (nodes, sorted
+        triangles) so a checker can be fed the same bytes."""
+        nodes, perm = build_bvh(scene.triangles)
+        sorted_tris = scene.triangles[perm]
+        self.upload_scene(sorted_tris, scene.materials, nodes)
+        return nodes, sorted_tris
+
+    # -- frames -----------------------------------------------------------
+    def render_frame(self, settings: np.ndarray, camera: np.ndarray) -> None:
+        rs = np.ascontiguousarray(settings, RENDER_SETTINGS_DTYPE)
+        cam = np.ascontiguousarray(camera, np.float32)
+        assert cam.size == 20
+        self._check(self._lib.rvpt_b200_render_frame(self._ctx, rs.ctypes.data, cam.ctypes.data))
+
+    def render_frame_raw(self, settings_ptr: int, camera_ptr: int) -> None:
+        self._check(self._lib.rvpt_b200_render_frame(self._ctx, settings_ptr, camera_ptr))
+
+    def sync(self) -> None:
+        self._check(self._lib.rvpt_b200_sync(self._ctx))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._check(self._lib.rvpt_b200_set_stream(self._ctx, cuda_stream))
+
+    def reset_accum(self) -> None:
+        self._check(self._lib.rvpt_b200_reset_accum(self._ctx))
+
+    # -- read-back --------------------------------------------------------
+    def read_output_rgba8(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
+        self._check(self._lib.rvpt_b200_read_output_rgba8(self._ctx, out.ctypes.data))
+        return out
+
+    def read_accum_f32(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self._lib.rvpt_b200_read_accum_f32(self._ctx, out.ctypes.data))
+        return out
+
+    def write_accum_f32(self, accum: np.ndarray) -> None:
+        a = np.ascontiguousarray(accum, np.float32)
+        assert a.shape == (self.height, self.width, 4)
+        self._check(self._lib.rvpt_b200_write_accum_f32(self._ctx, a.ctypes.data))
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        self._check(self._lib.rvpt_b200_get_stats(self._ctx, C.byref(st)))
+        active = [int(v) for v in st.active]
+        while active and active[-1] == 0:
+            active.pop()
+        return {"samples": int(st.samples), "segments": int(st.segments), "active": active,
+                "kernel_launches": int(st.kernel_launches)}
+
+    # -- multi-GPU tiles --------------------------------------------------
+    def tile_info(self) -> _lib.TileInfo:
+        ti = _lib.TileInfo()
+        self._check(self._lib.rvpt_b200_get_tile_info(self._ctx, C.byref(ti)))
+        return ti
+
+    def set_external_tiles(self, d_accum: int | None, d_rgba8: int | None) -> None:
+        self._check(self._lib.rvpt_b200_set_external_tiles(self._ctx, d_accum, d_rgba8))
+
+    def untile(self, d_gathered: int, d_raster: int, elem_bytes: int) -> None:
+        self._check(self._lib.rvpt_b200_untile(self._ctx, d_gathered, d_raster, elem_bytes,
+                                               self.nranks))
