@@ -69,8 +69,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 {
     uint32_t done = 0;
+    uint32_t spins = 0;
     while (!done)
     {
+        /* a copy that never lands must not hang the GPU: fail the launch instead */
+        if (++spins > (1u << 24)) __trap();
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -1,0 +1,268 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle on
+the same seeded inputs. The RNG is a pure function of (x, y, W, frame), so
+"same seed" = same settings/camera. Bar: BIT-EXACT float32 radiance (tolerance
+stated by BASELINE.json is 1e-4 relative; the shared arithmetic contract of
+include/rvpt_math.h lets us hold the stronger bar) and identical rgba8 codes.
+"""
+import numpy as np
+import pytest
+
+from conftest import CORNELL_POSE, DEFAULT_POSE, PINNED_POSE
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_both(rv, oracle_mod, prep, W, H, pose, frames=1, flags=0, oracle_flags=None, fov=90.0,
+                 nodes="bvh", **settings_kw):
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    eng = rv.Engine(W, H, flags=flags)
+    if nodes == "bvh":
+        eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    else:
+        eng.upload_scene(prep.triangles, prep.materials, None)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes,
+                                    flags=flags if oracle_flags is None else oracle_flags)
+    stats = []
+    for f in range(frames):
+        rs = rv.default_settings(frame=f, **settings_kw)
+        eng.render_frame(rs, cam)
+        ora.render_frame(rs, cam)
+        stats.append((eng.stats(), ora.active_list()))
+    return eng, ora, stats
+
+
+def _assert_bit_equal(a, b, what):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    same = a.view(np.uint32) == b.view(np.uint32)
+    if not same.all():
+        bad = np.argwhere(~same)
+        rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+        raise AssertionError(
+            f"{what}: {len(bad)} of {same.size} float32 words differ; first at {bad[0]}, "
+            f"gpu={a[tuple(bad[0])]!r} oracle={b[tuple(bad[0])]!r}, max rel err {np.nanmax(rel):.3e}")
+
+
+@pytest.mark.parametrize("pose", [DEFAULT_POSE, PINNED_POSE])
+def test_c1_builtin_256_bit_exact(rv, oracle_mod, builtin, pose):
+    """BASELINE config 1: built-in scene, 256x256, 1 spp, frame 0."""
+    eng, ora, stats = _render_both(rv, oracle_mod, builtin, 256, 256, pose)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "accum")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    st, active = stats[0]
+    assert st["active"] == active, "per-bounce ray counts must match the oracle"
+    assert st["samples"] == 256 * 256
+
+
+def test_progressive_frames_and_rel_tolerance(rv, oracle_mod, builtin):
+    """8 progressive frames; also states the north-star tolerance explicitly."""
+    eng, ora, stats = _render_both(rv, oracle_mod, builtin, 320, 180, (-0.13, 0.83, -1.6), frames=8)
+    g, o = eng.read_accum_f32(), ora.accum
+    rel = np.abs(g - o) / np.maximum(np.abs(o), 1e-6)
+    assert rel.max() <= 1e-4  # BASELINE.json north_star tolerance
+    _assert_bit_equal(g, o, "accum after 8 frames")
+    for st, active in stats:
+        assert st["active"] == active
+
+
+def test_cornell_mirror_dielectric_bit_exact(rv, oracle_mod, cornell):
+    """BASELINE config 3 shape: emissive light, mirror and dielectric blocks."""
+    eng, ora, stats = _render_both(rv, oracle_mod, cornell, 200, 152, CORNELL_POSE, frames=3, fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "cornell accum")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    st, active = stats[-1]
+    assert st["active"] == active
+    assert len(active) == 8 and active[7] > 0, "the Cornell scene must exercise all 8 bounces"
+
+
+def test_aa_passes_continue_the_rng_stream(rv, oracle_mod, cornell):
+    """aa > 1: sample i+1 of a pixel continues the xorshift stream of sample i
+    (compute_pass.comp:151-158)."""
+    eng, ora, stats = _render_both(rv, oracle_mod, cornell, 96, 80, CORNELL_POSE, frames=2, aa=3, fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "aa=3 accum")
+    st, active = stats[-1]
+    assert st["active"] == active
+    assert st["samples"] == 96 * 80 * 3
+
+
+@pytest.mark.parametrize("bounces", [1, 2, 16])
+def test_bounce_limits(rv, oracle_mod, cornell, bounces):
+    eng, ora, stats = _render_both(rv, oracle_mod, cornell, 64, 48, CORNELL_POSE, max_bounces=bounces, fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"max_bounces={bounces}")
+    assert stats[0][0]["active"] == stats[0][1]
+
+
+@pytest.mark.parametrize("camera_mode", [1, 2])
+def test_ortho_and_spherical_cameras(rv, oracle_mod, builtin, camera_mode):
+    eng, ora, _ = _render_both(rv, oracle_mod, builtin, 128, 64, (0.0, 0.8, -2.5), camera_mode=camera_mode)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"camera_mode={camera_mode}")
+
+
+def test_rgba8_accumulation_mode(rv, oracle_mod, builtin):
+    """Reference-faithful UNORM8 temporal image (rvpt.cpp:759-766): codes must
+    be identical (the stated tolerance for a real Vulkan run is 1 LSB)."""
+    from rvpt_b200 import _lib
+    eng, ora, _ = _render_both(rv, oracle_mod, builtin, 160, 96, PINNED_POSE, frames=5,
+                               flags=_lib.FLAG_ACCUM_RGBA8)
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    assert np.array_equal(eng.read_accum_f32(), ora.accum_f32())
+
+
+def test_reference_dispatch_truncation(rv, oracle_mod, builtin):
+    """W/16 x H/16 groups with integer division (rvpt.cpp:1035-1036): the
+    remainder rows/columns are never written."""
+    from rvpt_b200 import _lib
+    W, H = 200, 90  # 12 x 5 groups -> 192 x 80 covered
+    eng, ora, stats = _render_both(rv, oracle_mod, builtin, W, H, PINNED_POSE,
+                                   flags=_lib.FLAG_REFERENCE_DISPATCH)
+    g = eng.read_accum_f32()
+    _assert_bit_equal(g, ora.accum, "reference dispatch")
+    assert not g[80:].any() and not g[:, 192:].any()
+    assert stats[0][0]["samples"] == 192 * 80
+
+
+def test_brute_force_flag_and_internal_bvh(rv, oracle_mod, builtin):
+    """BVH traversal only prunes: list-order nearest hit gives the same image
+    on this scene; so does the BVH built inside upload_scene(nodes=NULL)."""
+    from rvpt_b200 import _lib
+    eng_bvh, ora, _ = _render_both(rv, oracle_mod, builtin, 128, 128, DEFAULT_POSE)
+    eng_bf, ora_bf, _ = _render_both(rv, oracle_mod, builtin, 128, 128, DEFAULT_POSE,
+                                     flags=_lib.FLAG_BRUTE_FORCE)
+    eng_int, _, _ = _render_both(rv, oracle_mod, builtin, 128, 128, DEFAULT_POSE, nodes="internal")
+    _assert_bit_equal(eng_bf.read_accum_f32(), ora_bf.accum, "brute force vs oracle brute force")
+    _assert_bit_equal(eng_bf.read_accum_f32(), eng_bvh.read_accum_f32(), "brute force vs BVH")
+    # internal build permutes the already-permuted triangles again; image is order independent here
+    _assert_bit_equal(eng_int.read_accum_f32(), eng_bvh.read_accum_f32(), "internal BVH")
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_tile_partition_reassembles_single_gpu_image(rv, builtin, nranks):
+    """Multi-GPU sharding without N GPUs: the ranks' tile sets,
+    rendered one after the other on this GPU, add up to the 1-GPU image bit
+    for bit — global (x, y, W) seed the RNG (util.glsl:35-36)."""
+    W, H = 208, 120  # ragged: 13 x 7.5 tiles
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    full = rv.Engine(W, H)
+    full.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    acc = np.zeros((H, W, 4), np.float32)
+    out = np.zeros((H, W, 4), np.uint8)
+    total_samples = 0
+    for f in range(2):
+        full.render_frame(rv.default_settings(frame=f), cam)
+    for r in range(nranks):
+        eng = rv.Engine(W, H, rank=r, nranks=nranks)
+        eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+        for f in range(2):
+            eng.render_frame(rv.default_settings(frame=f), cam)
+        a = eng.read_accum_f32()
+        o = eng.read_output_rgba8()
+        acc += a  # disjoint supports: other ranks' pixels are exactly 0
+        out += o
+        total_samples += eng.stats()["samples"]
+        eng.close()
+    _assert_bit_equal(acc, full.read_accum_f32(), f"{nranks}-rank reassembly")
+    assert np.array_equal(out, full.read_output_rgba8())
+    assert total_samples == W * H
+
+
+def test_checkpoint_resume_roundtrip(rv, oracle_mod, builtin):
+    W, H = 144, 80
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    a = rv.Engine(W, H)
+    a.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    for f in range(3):
+        a.render_frame(rv.default_settings(frame=f), cam)
+    snap = a.read_accum_f32()
+    b = rv.Engine(W, H)
+    b.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    b.write_accum_f32(snap)
+    _assert_bit_equal(b.read_accum_f32(), snap, "write/read accum")
+    for eng in (a, b):
+        eng.render_frame(rv.default_settings(frame=3), cam)
+    _assert_bit_equal(b.read_accum_f32(), a.read_accum_f32(), "resumed frame")
+
+
+def test_device_arithmetic_matches_host_header(rv, oracle_mod):
+    """include/rvpt_math.h evaluated on the device == on the host, bit for bit,
+    and -fmad=false was honoured."""
+    import ctypes as C
+    lib = rv._lib.load()
+    ol = oracle_mod.load()
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(0, 2 * np.pi, 20000), rng.uniform(-50, 50, 5000),
+                        [0.0, np.pi, 2 * np.pi, 6.2831855]]).astype(np.float32)
+    out = np.zeros((len(x), 2), np.float32)
+    assert lib.rvpt_b200_selftest_math(0, 0, x.ctypes.data, len(x), out.ctypes.data) == 0
+    s = np.zeros(len(x), np.float32)
+    c = np.zeros(len(x), np.float32)
+    ol.rvpt_oracle_sincos(x.ctypes.data, len(x), s.ctypes.data, c.ctypes.data)
+    assert np.array_equal(out[:, 0].view(np.uint32), s.view(np.uint32))
+    assert np.array_equal(out[:, 1].view(np.uint32), c.view(np.uint32))
+
+    v = rng.normal(size=(4096, 3)).astype(np.float32)
+    nout = np.zeros_like(v)
+    nref = np.zeros_like(v)
+    assert lib.rvpt_b200_selftest_math(0, 2, v.ctypes.data, len(v), nout.ctypes.data) == 0
+    ol.rvpt_oracle_normalize(v.ctypes.data, len(v), nref.ctypes.data)
+    assert np.array_equal(nout.view(np.uint32), nref.view(np.uint32))
+
+    probe = np.array([[1.0001220703125, 0.9998779296875, -1.0, np.pi / 2]], np.float32)
+    pout = np.zeros((1, 2), np.float32)
+    assert lib.rvpt_b200_selftest_math(0, 3, probe.ctypes.data, 1, pout.ctypes.data) == 0
+    assert pout[0, 0] == 1.0, "device code was compiled with FMA contraction"
+
+    seeds = rng.integers(1, 2**32, size=1024, dtype=np.uint32)
+    rout = np.zeros((len(seeds), 2), np.float32)
+    assert lib.rvpt_b200_selftest_math(0, 1, seeds.view(np.float32).ctypes.data, len(seeds),
+                                       rout.ctypes.data) == 0
+    s0 = seeds.copy()
+    for k in range(2):
+        s0 ^= s0 << np.uint32(13)
+        s0 ^= s0 >> np.uint32(17)
+        s0 ^= s0 << np.uint32(5)
+        assert np.array_equal(rout[:, k], s0.astype(np.float32) / np.float32(4294967296.0))
+
+
+def test_unsupported_and_error_paths(rv, builtin):
+    eng = rv.Engine(64, 64)
+    with pytest.raises(rv.EngineError) as e:
+        eng.render_frame(rv.default_settings(), rv.camera_data())
+    assert e.value.code == -3  # no scene
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    with pytest.raises(rv.EngineError) as e:
+        eng.render_frame(rv.default_settings(mode=3), rv.camera_data())
+    assert e.value.code == -4  # only Kajiya is on the hot path
+    bad = builtin.triangles.copy()
+    bad["material_id"][5, 0] = 7
+    with pytest.raises(rv.EngineError):
+        eng.upload_scene(bad, builtin.materials, builtin.nodes)
+    nodes = builtin.nodes.copy()
+    nodes["first_child_or_primitive"][0] = 0  # root is its own child: a cycle
+    with pytest.raises(rv.EngineError):
+        eng.upload_scene(builtin.triangles, builtin.materials, nodes)
+
+
+def test_full_size_1080p_properties(rv, oracle_mod, builtin):
+    """BASELINE config 2 at full size: a band of rows against the oracle,
+    sample count, and frame-order independence of the tile scheduler (two
+    engines, same frames -> identical images: no float atomics anywhere)."""
+    W, H = 1920, 1080
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    e1 = rv.Engine(W, H)
+    e1.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    e2 = rv.Engine(W, H)
+    e2.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+    y0, y1 = 500, 532
+    for f in range(3):
+        rs = rv.default_settings(frame=f)
+        e1.render_frame(rs, cam)
+        e2.render_frame(rs, cam)
+        ora.render_frame(rs, cam, y0, y1)
+    g = e1.read_accum_f32()
+    _assert_bit_equal(g[y0:y1], ora.accum[y0:y1], "1080p rows 500..531")
+    _assert_bit_equal(g, e2.read_accum_f32(), "determinism across engines")
+    st = e1.stats()
+    assert st["samples"] == W * H
+    assert st["segments"] == sum(st["active"])
+    assert g[1079].any(), "rows >= 1072 are rendered unless REFERENCE_DISPATCH is set"
