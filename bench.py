@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the path-tracing hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): built-in scene (143-triangle bunny,
+white Lambert, procedural sky; src/rvpt/main.cpp:102-107), literal default
+camera, 1920x1080, max_bounces 8, aa 1, progressive accumulation. One STEP is a
+progressive batch of `--frames` frames (default 16 spp): frame counter 0..F-1,
+so every step restarts the running mean (compute_pass.comp:146-148 multiplies
+the previous image by min(frame,1)).
+
+  value  device-resident throughput: scene uploaded once, frames launched back
+         to back through the C ABI, CUDA events on the launch stream.
+  e2e    the same step through the host-buffer API: upload_scene from host
+         arrays, F x render_frame (settings + camera by value), read back the
+         rgba8 result into pinned host memory — all inside the timed region.
+
+N > 1 (one process per GPU, NCCL): the frame is sharded by 16x16 pixel tile
+(tile_id % N == rank), every rank renders its tiles, and ONE all-gather of the
+rgba8 tiles per frame assembles the image on every rank (in place: the kernels
+write straight into the rank's slot of the gather buffer). Total work is fixed
+("scaling": "strong").
+
+--impl reference times the CPU restatement of the reference shader
+(oracle/rvpt_oracle.cpp — the reference's Vulkan path cannot run here, see
+DESIGN.md) with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Msamples/s at 1920x1080, 8-bounce, built-in scene"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--frames", type=int, default=16, help="progressive frames (spp) per step")
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--aa", type=int, default=1)
+    ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell"])
+    ap.add_argument("--pose", default="default", choices=["default", "pinned"])
+    ap.add_argument("--gather", default="rgba8", choices=["rgba8", "none"])
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    import rvpt_b200 as rv
+    if args.scene == "builtin":
+        scene = rv.builtin_scene()
+        pose = (0.0, 0.0, 0.0) if args.pose == "default" else (0.0, 0.8, -2.5)
+        fov = 90.0
+    else:
+        scene = rv.cornell_scene()
+        pose, fov = (0.0, 1.2, -3.4), 60.0
+    nodes, perm = rv.build_bvh(scene.triangles)
+    tris = np.ascontiguousarray(scene.triangles[perm])
+    cam = rv.camera_data(translation=pose, aspect=args.width / args.height, fov=fov)
+    name = (f"C2 {args.scene} scene ({len(tris)} triangles, {len(nodes)} BVH nodes), "
+            f"{args.pose} pose, {args.width}x{args.height}, max_bounces {args.bounces}, aa {args.aa}")
+    return rv, scene, nodes, tris, cam, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_rate(args, nodes, tris, mats, cam, seconds: float, nthreads: int = 0):
+    """Times the CPU oracle on a bounded sample of the workload: a centred band
+    of rows of frame 0.., grown until ~`seconds` of work. Returns (Msamples/s,
+    cores, description)."""
+    import oracle
+    rvsettings = __import__("rvpt_b200").default_settings
+    W, H = args.width, args.height
+    ora = oracle.OracleRenderer(W, H, tris, mats, nodes, nthreads=nthreads)
+    cores = nthreads or oracle.load().rvpt_oracle_hardware_threads()
+    # calibrate on 64 centred rows
+    y0 = max(0, H // 2 - 32)
+    y1 = min(H, y0 + 64)
+    t = time.perf_counter()
+    ora.render_frame(rvsettings(max_bounces=args.bounces, aa=args.aa, frame=0), cam, y0, y1)
+    dt = time.perf_counter() - t
+    rate = (y1 - y0) * W * args.aa / dt
+    # bounded sample: whole frames, as many as fit the budget (at least one)
+    frames = int(max(1, min(64, seconds * rate / (W * H * args.aa))))
+    ora = oracle.OracleRenderer(W, H, tris, mats, nodes, nthreads=nthreads)
+    t = time.perf_counter()
+    for f in range(frames):
+        ora.render_frame(rvsettings(max_bounces=args.bounces, aa=args.aa, frame=f), cam)
+    dt = time.perf_counter() - t
+    msps = frames * W * H * args.aa / dt / 1e6
+    return msps, cores, f"{frames} full frame(s) of the workload, {dt:.1f} s on {cores} threads"
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference shader on the box's
+    host cores (kind "port": the Vulkan path cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rv, scene, nodes, tris, cam, name = workload(args)
+    import oracle
+    W, H = args.width, args.height
+    cores = oracle.load().rvpt_oracle_hardware_threads()
+    ora = oracle.OracleRenderer(W, H, tris, scene.materials, nodes)
+    # one step = one full frame of the workload (bounded sample of the 16-frame step)
+    frame = 0
+
+    def step():
+        nonlocal frame
+        ora.render_frame(rv.default_settings(max_bounces=args.bounces, aa=args.aa, frame=frame), cam)
+        frame += 1
+
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t
+    msps = args.steps * W * H * args.aa / dt / 1e6
+    sample = f"each step = 1 full frame ({W}x{H}x{args.aa} samples) of the workload"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": msps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": name, "sample": sample},
+        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rv, scene, nodes, tris, cam, name = workload(args)
+    W, H, F = args.width, args.height, args.frames
+    eng = rv.Engine(W, H, device=local_rank, rank=rank, nranks=world)
+    # a real (non-default) stream shared by torch and the engine, so torch's CUDA
+    # events bracket exactly the kernels the C ABI launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng.set_stream(stream.cuda_stream)
+    eng.upload_scene(tris, scene.materials, nodes)
+
+    settings = [rv.default_settings(max_bounces=args.bounces, aa=args.aa, frame=f) for f in range(F)]
+    settings_ptr = [s.ctypes.data for s in settings]
+    cam_ptr = cam.ctypes.data
+
+    # multi-GPU: kernels write rgba8 tiles straight into this rank's slot of the gather buffer
+    gathered = raster = None
+    gather = world > 1 and args.gather == "rgba8"
+    if world > 1:
+        ti = eng.tile_info()
+        slot_elems = ti.n_local_tiles_padded * 256
+        gathered = torch.zeros(world * slot_elems, dtype=torch.int32, device="cuda")
+        raster = torch.zeros(H * W, dtype=torch.int32, device="cuda")
+        my_slot = gathered[rank * slot_elems:(rank + 1) * slot_elems]
+        eng.set_external_tiles(None, my_slot.data_ptr())
+
+    def frames_of_step():
+        for f in range(F):
+            eng.render_frame_raw(settings_ptr[f], cam_ptr)
+            if gather:
+                dist.all_gather_into_tensor(gathered, my_slot)
+                if rank == 0:
+                    eng.untile(gathered.data_ptr(), raster.data_ptr(), 4)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # 2x L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        frames_of_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()              # evict the accumulation image from L2 between steps
+        if world > 1:
+            dist.barrier()
+        starts[k].record(stream)
+        frames_of_step()
+        ends[k].record(stream)
+    barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    st = eng.stats()
+    launches_per_frame = st["kernel_launches"] + (1 if (gather and rank == 0) else 0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    samples_per_step = W * H * args.aa * F
+    value = args.steps * samples_per_step / (total_ms * 1e-3) / 1e6
+
+    # ---- per-kernel timing for the roofline (separate pass, same workload) --------------
+    eng.set_profiling(True)
+    eng.kernel_times()
+    for _ in range(2):
+        flush.zero_()
+        for f in range(F):
+            eng.render_frame_raw(settings_ptr[f], cam_ptr)
+    kt = eng.kernel_times()
+    eng.set_profiling(False)
+    active = st["active"] + [0] * 64
+    S_local = st["samples"]
+    R = sum(active)
+    # DESIGN.md "algorithmic bytes": a terminated sample reads + writes the float4 running
+    # mean and writes rgba8 (36 B); every segment after the first writes and re-reads the
+    # 64 B path state (128 B). SURVEY 8(d)'s 128R + 36S additionally charges the primary
+    # ray a state round trip that the fused generation + bounce-0 wave never makes.
+    frame_bytes = 36 * S_local + 128 * (R - S_local)
+    survey_bytes = 128 * R + 36 * S_local
+    kernel_ms = kt["primary_ms"] / max(kt["primary_launches"], 1)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
+    else:
+        peak, peak_src = 6650.0, "fallback"
+    achieved = frame_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    frame_ms = total_ms / (args.steps * F)
+    roofline = {
+        "bound": "hbm", "kernel": "k_frame (one persistent cooperative launch per frame: primary "
+                                  "wave + bounce waves + in-place accumulation)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": None,
+        "bytes_per_launch": frame_bytes, "ms_per_launch": kernel_ms,
+        "survey_8d_formula_bytes": survey_bytes,
+        "survey_8d_formula_gbs": survey_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
+        "frame_ms_in_timed_region": frame_ms,
+        "rays_per_sample": R / max(S_local, 1), "active_per_bounce": st["active"],
+        "note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md); inside a step the "
+                "41.5 MB accumulation working set is L2-resident (126 MB L2); L2 is flushed "
+                "between steps",
+    }
+
+    # ---- end to end through the host-buffer API -----------------------------------------
+    out_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    out_np = out_pinned.numpy()
+    mats = scene.materials
+    scene_h2d = nodes.nbytes + tris.nbytes + mats.nbytes
+    h2d = scene_h2d + F * (40 + 80)
+    d2h = W * H * 4
+
+    def e2e_step():
+        eng.upload_scene(tris, mats, nodes)           # host arrays -> device, every step
+        frames_of_step()
+        if world == 1:
+            eng.read_output_rgba8(out_np)              # device -> pinned host, synchronises
+        else:
+            if rank == 0:
+                out_pinned.view(torch.int32).view(-1).copy_(raster, non_blocking=False)
+            else:
+                torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * samples_per_step / float(e2e_s.item()) / 1e6
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        msps, cores, sample = oracle_rate(args, nodes, tris, mats, cam, args.cpu_baseline_seconds)
+        cpu = {"value": msps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": name, "frames_per_step": F, "samples_per_step": samples_per_step,
+                       "partition": f"16x16 tiles, tile_id % {world} == rank" if world > 1 else "none",
+                       "gather": ("rgba8 all_gather_into_tensor per frame + untile on rank 0"
+                                  if gather else "none"),
+                       "l2": "256 MiB memset between steps (outside the timed events); "
+                             "frames inside a step share L2 as in the real render loop"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "what": "upload_scene(host arrays) + F x render_frame + read_output_rgba8 "
+                            "into pinned memory, wall clock incl. synchronisation"},
+            "gpu_launches": args.steps * F * launches_per_frame,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "mrays_per_s": value * (R / max(S_local, 1)),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,10 @@ typedef struct rvpt_b200_stats
 /* Ignore the BVH and test every triangle in upload order (legacy
  * intersect_triangles semantics; used to cross-check BVH traversal). */
 #define RVPT_B200_FLAG_BRUTE_FORCE 0x4u
+/* Launch every wave (primary, bounce 1, bounce 2, ...) as its own kernel
+ * instead of the single persistent cooperative kernel per frame. Same results;
+ * used for per-wave profiling and as a cross-check of the fused kernel. */
+#define RVPT_B200_FLAG_UNFUSED 0x8u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 
@@ -193,6 +197,21 @@ RVPT_API int rvpt_b200_write_accum_f32(rvpt_b200_ctx* ctx, const float* src);
 RVPT_API int rvpt_b200_reset_accum(rvpt_b200_ctx* ctx);
 /* Counters of the most recent frame (synchronises). */
 RVPT_API int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out);
+
+/* Per-kernel device timing (the reference's only counter is the wall-clock
+ * Timer around draw(), rvpt.cpp:348,403). While enabled every kernel launch is
+ * bracketed by CUDA events on the ctx stream; get_kernel_times() synchronises,
+ * returns the sums since the last call and clears them. Serialises nothing,
+ * but the event records cost a little: keep it off for throughput runs. */
+typedef struct rvpt_b200_kernel_times
+{
+    double primary_ms;      /* k_frame (whole frame), or k_primary when UNFUSED */
+    double bounce_ms;       /* k_bounce launches (UNFUSED only) */
+    uint32_t primary_launches;
+    uint32_t bounce_launches;
+} rvpt_b200_kernel_times;
+RVPT_API int rvpt_b200_set_profiling(rvpt_b200_ctx* ctx, int enabled);
+RVPT_API int rvpt_b200_get_kernel_times(rvpt_b200_ctx* ctx, rvpt_b200_kernel_times* out);
 
 /* ------------------------------------------------------------------------ */
 /* Device-side tile buffers, for the multi-GPU gather (NCCL runs in the      */

@@ -14,6 +14,7 @@ MAX_BOUNCE_STATS = 64
 FLAG_ACCUM_RGBA8 = 0x1
 FLAG_REFERENCE_DISPATCH = 0x2
 FLAG_BRUTE_FORCE = 0x4
+FLAG_UNFUSED = 0x8
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -25,6 +26,13 @@ class Stats(C.Structure):
         ("active", C.c_uint64 * MAX_BOUNCE_STATS),
         ("kernel_launches", C.c_uint32),
         ("reserved", C.c_uint32),
+    ]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [
+        ("primary_ms", C.c_double), ("bounce_ms", C.c_double),
+        ("primary_launches", C.c_uint32), ("bounce_launches", C.c_uint32),
     ]
 
 
@@ -55,6 +63,8 @@ SIGNATURES = {
     "rvpt_b200_write_accum_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_reset_accum": (C.c_int, [C.c_void_p]),
     "rvpt_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "rvpt_b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "rvpt_b200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTimes)]),
     "rvpt_b200_get_tile_info": (C.c_int, [C.c_void_p, C.POINTER(TileInfo)]),
     "rvpt_b200_set_external_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvpt_b200_untile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),

@@ -88,15 +88,27 @@ struct PathQueue
     float4* q3;
 };
 
-/* Device counters, zeroed per pass (first block) / per frame (stats). */
+/*
+ * Device counters. Two sets of each, used alternately, so no memset is ever
+ * launched: the kernel of launch L zeroes the wave set of launch L+1, and the
+ * first pass of frame F zeroes the stats set of frame F+1 (whose previous user,
+ * launch L-1 / frame F-1, has completed in stream order).
+ */
+struct WaveCounters
+{
+    uint32_t chunk_ctr;    /* primary phase work distribution */
+    uint32_t pad0[3];
+    uint32_t work_ctr[64]; /* bounce phase work distribution, per bounce */
+    uint32_t qcount[64];   /* survivors pushed by bounce b (read by b+1) */
+};
+struct FrameStats
+{
+    unsigned long long active[64]; /* rays traced at bounce b, whole frame (all aa passes) */
+};
 struct FrameCounters
 {
-    uint32_t chunk_ctr;                 /* k_primary work distribution */
-    uint32_t pad0[3];
-    uint32_t work_ctr[64];              /* k_bounce work distribution, per bounce */
-    uint32_t qcount[64];                /* survivors pushed by bounce b (read by b+1) */
-    /* ---- not cleared between aa passes ---- */
-    unsigned long long active[64];      /* rays traced at bounce b, whole frame */
+    WaveCounters wave[2];
+    FrameStats stats[2];
 };
 
 /* Per-frame constants, passed by value as a kernel parameter. */
@@ -138,6 +150,9 @@ struct FrameParams
     uchar4* out_raster;           /* rgba8 result, raster (nranks == 1) */
     float4* carry;                /* per-slot (sum.xyz, rng) between aa passes */
     FrameCounters* ctr;
+    uint32_t wave_set;            /* launch sequence parity */
+    uint32_t stats_set;           /* frame sequence parity */
+    uint32_t tail_threshold;      /* waves this small finish inside their threads */
 };
 
 #endif

@@ -42,7 +42,9 @@ struct rvpt_b200_ctx
     uint32_t rank = 0, nranks = 1;
     uint32_t n_local_tiles = 0, n_local_padded = 0;
     int num_sms = 0;
-    int grid_primary = 0, grid_bounce = 0;
+    int grid_frame = 0, grid_primary = 0, grid_bounce = 0;
+    uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
+    uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -68,6 +70,17 @@ struct rvpt_b200_ctx
     int last_max_bounces = 0;
     int last_aa = 0;
     uint32_t last_launches = 0;
+    uint32_t last_stats_set = 0;
+
+    /* per-kernel timing */
+    bool profiling = false;
+    struct Timed
+    {
+        cudaEvent_t a, b;
+        int kind; /* 0 primary, 1 bounce */
+    };
+    std::vector<Timed> timed;      /* recorded, not yet collected */
+    std::vector<Timed> event_pool; /* recycled */
 
     std::string err;
 };
@@ -177,6 +190,37 @@ void recompute_partition(rvpt_b200_ctx* ctx)
     ctx->n_local_tiles =
         ctx->rank < ctx->n_tiles ? (ctx->n_tiles - ctx->rank + ctx->nranks - 1) / ctx->nranks : 0;
 }
+
+/* ---- per-kernel timing ----------------------------------------------------- */
+
+struct ScopedTimer
+{
+    rvpt_b200_ctx* ctx;
+    rvpt_b200_ctx::Timed t{};
+    bool on;
+    ScopedTimer(rvpt_b200_ctx* c, int kind) : ctx(c), on(c->profiling)
+    {
+        if (!on) return;
+        if (!ctx->event_pool.empty())
+        {
+            t = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+        }
+        else if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess)
+        {
+            on = false;
+            return;
+        }
+        t.kind = kind;
+        cudaEventRecord(t.a, ctx->stream);
+    }
+    ~ScopedTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(t.b, ctx->stream);
+        ctx->timed.push_back(t);
+    }
+};
 
 /* ---- scene packing -------------------------------------------------------- */
 
@@ -368,12 +412,14 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     ctx->layout = L;
     ctx->scene_smem = L.bytes <= RVPT_SMEM_SCENE_LIMIT;
 
-    int occ_p = 0, occ_b = 0;
+    int occ_f = 0, occ_p = 0, occ_b = 0;
     if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
-    CU(rvpt::occupancy(&occ_p, &occ_b, ctx->scene_smem, L.bytes));
-    if (occ_p < 1 || occ_b < 1)
-        return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d)", occ_p,
-                    occ_b);
+    CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes));
+    if (occ_f < 1 || occ_p < 1 || occ_b < 1)
+        return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)", occ_f,
+                    occ_p, occ_b);
+    /* persistent grids: every CTA is resident (a requirement of the cooperative launch) */
+    ctx->grid_frame = ctx->num_sms * occ_f;
     ctx->grid_primary = ctx->num_sms * occ_p;
     ctx->grid_bounce = ctx->num_sms * occ_b;
     ctx->have_scene = true;
@@ -410,7 +456,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (width == 0 || height == 0 || width > 65536 || height > 65536)
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
-                  RVPT_B200_FLAG_BRUTE_FORCE))
+                  RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     ctx->device = device;
     ctx->W = width;
@@ -446,6 +492,12 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
         cudaStreamSynchronize(ctx->stream);
         free_frame_buffers(ctx);
         cudaFree(ctx->d_scene);
+        for (auto& t : ctx->timed) ctx->event_pool.push_back(t);
+        for (auto& t : ctx->event_pool)
+        {
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
         cudaStreamDestroy(ctx->own_stream);
     }
     delete ctx;
@@ -566,23 +618,40 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
 
+    p.stats_set = ctx->frame_seq & 1u;
+    const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;
+    /* a wave with at most two rays per resident warp runs to completion in its threads */
+    p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * 2u;
+
     uint32_t launches = 0;
-    for (int pass = 0; pass < rs->aa; ++pass)
+    for (int pass = 0; pass < rs->aa && p.n_chunks > 0; ++pass)
     {
         p.pass = pass;
-        const size_t clear = pass == 0 ? sizeof(FrameCounters) : offsetof(FrameCounters, active);
-        CU(cudaMemsetAsync(ctx->d_ctr, 0, clear, ctx->stream));
-        if (p.n_chunks > 0)
+        p.wave_set = ctx->launch_seq & 1u;
+        if (!unfused)
         {
-            CU(rvpt::launch_primary(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
+            ScopedTimer tm(ctx, 0);
+            CU(rvpt::launch_frame(p, ctx->scene_smem, ctx->grid_frame, ctx->stream));
+            ++launches;
+        }
+        else
+        {
+            {
+                ScopedTimer tm(ctx, 0);
+                CU(rvpt::launch_primary(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
+            }
             ++launches;
             for (int b = 1; b < rs->max_bounces; ++b)
             {
+                ScopedTimer tm(ctx, 1);
                 CU(rvpt::launch_bounce(p, b, ctx->scene_smem, ctx->grid_bounce, ctx->stream));
                 ++launches;
             }
         }
+        ctx->launch_seq++;
     }
+    ctx->last_stats_set = p.stats_set;
+    ctx->frame_seq++;
     ctx->frame_rendered = true;
     ctx->last_max_bounces = rs->max_bounces;
     ctx->last_aa = rs->aa;
@@ -695,8 +764,9 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     std::memset(out, 0, sizeof(*out));
     if (!ctx->frame_rendered) return 0;
     CU(cudaSetDevice(ctx->device));
-    FrameCounters h;
-    CU(cudaMemcpyAsync(&h, ctx->d_ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FrameStats h;
+    CU(cudaMemcpyAsync(&h, &ctx->d_ctr->stats[ctx->last_stats_set], sizeof(h),
+                       cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < RVPT_MAX_BOUNCE_STATS; ++b)
     {
@@ -705,6 +775,33 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     }
     out->samples = ctx->last_max_bounces > 0 ? h.active[0] : 0;
     out->kernel_launches = ctx->last_launches;
+    return 0;
+}
+
+extern "C" int rvpt_b200_set_profiling(rvpt_b200_ctx* ctx, int enabled)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    ctx->profiling = enabled != 0;
+    return 0;
+}
+
+extern "C" int rvpt_b200_get_kernel_times(rvpt_b200_ctx* ctx, rvpt_b200_kernel_times* out)
+{
+    if (!ctx || !out) return RVPT_B200_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& t : ctx->timed)
+    {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        if (t.kind == 0)
+            out->primary_ms += ms, out->primary_launches++;
+        else
+            out->bounce_ms += ms, out->bounce_launches++;
+        ctx->event_pool.push_back(t);
+    }
+    ctx->timed.clear();
     return 0;
 }
 

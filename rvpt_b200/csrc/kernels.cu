@@ -18,6 +18,7 @@
  * Arithmetic follows include/rvpt_math.h (unfused float32, -fmad=false) so the
  * result is bit-identical to oracle/rvpt_oracle.cpp.
  */
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -446,29 +447,34 @@ __device__ __forceinline__ void camera_ray(const FrameParams& p, float cx, float
 }
 
 /* ======================================================================== */
-/* k_primary: generation + bounce 0                                          */
+/* phases                                                                    */
 /* ======================================================================== */
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    SceneView sc;
-    if (kSmem)
-    {
-        stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view(smem, p.layout);
-    }
-    else
-        sc = make_view(p.scene, p.layout);
 
+/* Launch L clears the counters of launch L+1 (and, on the first pass of a
+ * frame, the stats of the next frame). Nobody reads them during this launch. */
+__device__ __forceinline__ void clear_next_counters(const FrameParams& p)
+{
+    if (blockIdx.x != 0) return;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&p.ctr->wave[p.wave_set ^ 1u]);
+    for (uint32_t i = threadIdx.x; i < sizeof(WaveCounters) / 4; i += blockDim.x) w[i] = 0u;
+    if (p.pass == 0)
+    {
+        unsigned long long* a = p.ctr->stats[p.stats_set ^ 1u].active;
+        for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) a[i] = 0ull;
+    }
+}
+
+/* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
+__device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneView& sc)
+{
+    WaveCounters& wc = p.ctr->wave[p.wave_set];
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long traced = 0;
 
     for (;;)
     {
         uint32_t c0 = 0;
-        if (lane == 0) c0 = atomicAdd(&p.ctr->chunk_ctr, kChunkGrain);
+        if (lane == 0) c0 = atomicAdd(&wc.chunk_ctr, kChunkGrain);
         c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
         if (c0 >= p.n_chunks) break;
         const uint32_t c1 = min(c0 + kChunkGrain, p.n_chunks);
@@ -513,50 +519,38 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
             }
             if (p.max_bounces > 0)
                 traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
-            push_survivors(p, p.queue[0], &p.ctr->qcount[0], alive, slot, s);
+            push_survivors(p, p.queue[0], &wc.qcount[0], alive, slot, s);
         }
     }
-    if (lane == 0 && traced) atomicAdd(&p.ctr->active[0], traced);
+    if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
 }
 
-/* ======================================================================== */
-/* k_bounce: iteration b >= 1 over queue[(b-1)&1] -> queue[b&1]              */
-/* ======================================================================== */
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const int b)
+__device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathState& s,
+                                          uint32_t& slot)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    __shared__ uint32_t first_claim;
+    const float4 a0 = q.q0[i];
+    const float4 a1 = q.q1[i];
+    const float4 a2 = q.q2[i];
+    const float4 a3 = q.q3[i];
+    s.o = rv_make(a0.x, a0.y, a0.z);
+    slot = __float_as_uint(a0.w);
+    s.d = rv_make(a1.x, a1.y, a1.z);
+    s.rng = __float_as_uint(a1.w);
+    s.thr = rv_make(a2.x, a2.y, a2.z);
+    s.col = rv_make(a3.x, a3.y, a3.z);
+}
 
-    const uint32_t count = p.ctr->qcount[b - 1];
-    /* an empty wave costs one atomic per CTA and no scene staging */
-    if (threadIdx.x == 0)
-        first_claim = count ? atomicAdd(&p.ctr->work_ctr[b], 32u * kRayGrain * kWarpsPerCta) : count;
-    __syncthreads();
-    const uint32_t cta_first = first_claim;
-    if (cta_first >= count) return;
-    /* exactly one CTA claims offset 0: it records the wave size */
-    if (threadIdx.x == 0 && cta_first == 0 && b < RVPT_MAX_BOUNCE_STATS)
-        atomicAdd(&p.ctr->active[b], (unsigned long long)count);
-
-    SceneView sc;
-    if (kSmem)
-    {
-        stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view(smem, p.layout);
-    }
-    else
-        sc = make_view(p.scene, p.layout);
-
+/* iteration b >= 1 over queue[(b-1)&1] -> queue[b&1]; `r0` is the first ray
+ * group this warp already owns (claimed by its CTA), later ones are claimed
+ * per warp. */
+__device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneView& sc, int b,
+                                             uint32_t count, uint32_t r0)
+{
+    WaveCounters& wc = p.ctr->wave[p.wave_set];
     const PathQueue qin = p.queue[(b - 1) & 1];
     const PathQueue qout = p.queue[b & 1];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = threadIdx.x >> 5;
     const bool last_bounce = (b == p.max_bounces - 1);
-
-    /* the CTA-level claim is split evenly between its warps; later claims are per warp */
-    uint32_t r0 = cta_first + warp * 32u * kRayGrain;
     for (;;)
     {
         if (r0 >= count) break;
@@ -569,17 +563,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
             uint32_t slot = 0;
             if (i < count)
             {
-                const float4 a0 = qin.q0[i];
-                const float4 a1 = qin.q1[i];
-                const float4 a2 = qin.q2[i];
-                const float4 a3 = qin.q3[i];
-                s.o = rv_make(a0.x, a0.y, a0.z);
-                slot = __float_as_uint(a0.w);
-                s.d = rv_make(a1.x, a1.y, a1.z);
-                s.rng = __float_as_uint(a1.w);
-                s.thr = rv_make(a2.x, a2.y, a2.z);
-                s.col = rv_make(a3.x, a3.y, a3.z);
-
+                load_path(qin, i, s, slot);
                 rv_f3 sample;
                 alive = kajiya_step(sc, s, sample);
                 if (alive && last_bounce)
@@ -589,12 +573,134 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
                 }
                 if (!alive) finish_sample(p, slot, sample, s.rng);
             }
-            push_survivors(p, qout, &p.ctr->qcount[b], alive, slot, s);
+            push_survivors(p, qout, &wc.qcount[b], alive, slot, s);
         }
         uint32_t nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&p.ctr->work_ctr[b], 32u * kRayGrain);
+        if (lane == 0) nxt = atomicAdd(&wc.work_ctr[b], 32u * kRayGrain);
         r0 = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
+}
+
+/* A wave too small to fill the machine: ray i goes to warp (i % n_warps),
+ * lane (i / n_warps), so the few rays sit alone in their warps (no divergence
+ * serialisation) and every path runs to its end inside its thread. Counts the
+ * rays of the later bounces as it goes. */
+__device__ __forceinline__ void tail_phase(const FrameParams& p, const SceneView& sc, int b,
+                                           uint32_t count)
+{
+    const PathQueue qin = p.queue[(b - 1) & 1];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t i = lane * n_warps + gwarp;
+    if (i >= count) return;
+    PathState s;
+    uint32_t slot;
+    load_path(qin, i, s, slot);
+    rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
+    unsigned long long* active = p.ctr->stats[p.stats_set].active;
+    for (int k = b; k < p.max_bounces; ++k)
+    {
+        if (k > b && k < RVPT_MAX_BOUNCE_STATS) atomicAdd(&active[k], 1ull);
+        if (!kajiya_step(sc, s, sample)) break;
+        sample = rv_make(0.0f, 0.0f, 0.0f); /* still alive: black if the loop ends here */
+    }
+    finish_sample(p, slot, sample, s.rng);
+}
+
+/* ======================================================================== */
+/* k_frame: the whole frame (one aa pass) in ONE persistent cooperative launch */
+/* ======================================================================== */
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t first_claim;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+
+    clear_next_counters(p);
+    SceneView sc;
+    if (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view(smem, p.layout);
+    }
+    else
+        sc = make_view(p.scene, p.layout);
+
+    primary_phase(p, sc);
+
+    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    for (int b = 1; b < p.max_bounces; ++b)
+    {
+        grid.sync(); /* wave b-1 is complete: its survivor count is final */
+        const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&wc.qcount[b - 1]);
+        if (count == 0) break;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
+            atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
+        if (count <= p.tail_threshold)
+        {
+            tail_phase(p, sc, b, count);
+            break;
+        }
+        if (threadIdx.x == 0)
+            first_claim = atomicAdd(&wc.work_ctr[b], 32u * kRayGrain * kWarpsPerCta);
+        __syncthreads();
+        const uint32_t cta_first = first_claim;
+        __syncthreads(); /* first_claim is rewritten next wave */
+        bounce_phase(p, sc, b, count, cta_first + (threadIdx.x >> 5) * 32u * kRayGrain);
+    }
+}
+
+/* ======================================================================== */
+/* unfused variant: one launch per wave (profiling / cross-check)             */
+/* ======================================================================== */
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    clear_next_counters(p);
+    SceneView sc;
+    if (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view(smem, p.layout);
+    }
+    else
+        sc = make_view(p.scene, p.layout);
+    primary_phase(p, sc);
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const int b)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t first_claim;
+
+    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    const uint32_t count = wc.qcount[b - 1];
+    /* an empty wave costs one atomic per CTA and no scene staging */
+    if (threadIdx.x == 0)
+        first_claim = count ? atomicAdd(&wc.work_ctr[b], 32u * kRayGrain * kWarpsPerCta) : count;
+    __syncthreads();
+    const uint32_t cta_first = first_claim;
+    if (cta_first >= count) return;
+    /* exactly one CTA claims offset 0: it records the wave size */
+    if (threadIdx.x == 0 && cta_first == 0 && b < RVPT_MAX_BOUNCE_STATS)
+        atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
+
+    SceneView sc;
+    if (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view(smem, p.layout);
+    }
+    else
+        sc = make_view(p.scene, p.layout);
+    bounce_phase(p, sc, b, count, cta_first + (threadIdx.x >> 5) * 32u * kRayGrain);
 }
 
 /* ======================================================================== */
@@ -724,6 +830,9 @@ static size_t smem_bytes_for(const FrameParams& p, bool smem) { return smem ? p.
 cudaError_t configure_kernels(size_t max_dynamic_smem)
 {
     cudaError_t e;
+    e = cudaFuncSetAttribute(k_frame<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)max_dynamic_smem);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)max_dynamic_smem);
     if (e != cudaSuccess) return e;
@@ -732,13 +841,16 @@ cudaError_t configure_kernels(size_t max_dynamic_smem)
     return e;
 }
 
-cudaError_t occupancy(int* primary_ctas_per_sm, int* bounce_ctas_per_sm, bool smem,
-                      size_t scene_bytes)
+cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bounce_ctas_per_sm,
+                      bool smem, size_t scene_bytes)
 {
     const size_t dyn = smem ? scene_bytes : 0;
     cudaError_t e;
     if (smem)
     {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<true>, kThreads,
+                                                          dyn);
+        if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<true>,
                                                           kThreads, dyn);
         if (e != cudaSuccess) return e;
@@ -747,6 +859,9 @@ cudaError_t occupancy(int* primary_ctas_per_sm, int* bounce_ctas_per_sm, bool sm
     }
     else
     {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<false>,
+                                                          kThreads, dyn);
+        if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<false>,
                                                           kThreads, dyn);
         if (e != cudaSuccess) return e;
@@ -754,6 +869,16 @@ cudaError_t occupancy(int* primary_ctas_per_sm, int* bounce_ctas_per_sm, bool sm
                                                           kThreads, dyn);
     }
     return e;
+}
+
+cudaError_t launch_frame(const FrameParams& p, bool smem, int grid, cudaStream_t st)
+{
+    void* args[] = {const_cast<FrameParams*>(&p)};
+    if (smem)
+        return cudaLaunchCooperativeKernel((const void*)k_frame<true>, dim3(grid), dim3(kThreads),
+                                           args, smem_bytes_for(p, true), st);
+    return cudaLaunchCooperativeKernel((const void*)k_frame<false>, dim3(grid), dim3(kThreads), args,
+                                       0, st);
 }
 
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)

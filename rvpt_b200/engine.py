@@ -162,6 +162,15 @@ class Engine:
         return {"samples": int(st.samples), "segments": int(st.segments), "active": active,
                 "kernel_launches": int(st.kernel_launches)}
 
+    def set_profiling(self, enabled: bool) -> None:
+        self._check(self._lib.rvpt_b200_set_profiling(self._ctx, int(enabled)))
+
+    def kernel_times(self) -> dict:
+        kt = _lib.KernelTimes()
+        self._check(self._lib.rvpt_b200_get_kernel_times(self._ctx, C.byref(kt)))
+        return {"primary_ms": kt.primary_ms, "bounce_ms": kt.bounce_ms,
+                "primary_launches": kt.primary_launches, "bounce_launches": kt.bounce_launches}
+
     # -- multi-GPU tiles --------------------------------------------------
     def tile_info(self) -> _lib.TileInfo:
         ti = _lib.TileInfo()

@@ -135,6 +135,20 @@ def test_brute_force_flag_and_internal_bvh(rv, oracle_mod, builtin):
     _assert_bit_equal(eng_int.read_accum_f32(), eng_bvh.read_accum_f32(), "internal BVH")
 
 
+def test_unfused_waves_equal_fused_frame_kernel(rv, oracle_mod, cornell):
+    """One launch per wave (UNFUSED) and the persistent cooperative k_frame are
+    the same computation."""
+    from rvpt_b200 import _lib
+    eng_u, ora, stats = _render_both(rv, oracle_mod, cornell, 176, 128, CORNELL_POSE, frames=2,
+                                     flags=_lib.FLAG_UNFUSED, oracle_flags=0, fov=60.0)
+    _assert_bit_equal(eng_u.read_accum_f32(), ora.accum, "unfused")
+    assert stats[-1][0]["active"] == stats[-1][1]
+    assert stats[-1][0]["kernel_launches"] == 8
+    eng_f, _, stats_f = _render_both(rv, oracle_mod, cornell, 176, 128, CORNELL_POSE, frames=2, fov=60.0)
+    assert stats_f[-1][0]["kernel_launches"] == 1
+    _assert_bit_equal(eng_f.read_accum_f32(), eng_u.read_accum_f32(), "fused vs unfused")
+
+
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_tile_partition_reassembles_single_gpu_image(rv, builtin, nranks):
     """Multi-GPU sharding without N GPUs: the ranks' tile sets,
