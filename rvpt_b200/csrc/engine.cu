@@ -410,11 +410,11 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     CU(cudaMemcpyAsync(ctx->d_scene, blob.data(), L.bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); /* blob is a stack temporary */
     ctx->layout = L;
-    ctx->scene_smem = L.bytes <= RVPT_SMEM_SCENE_LIMIT;
+    ctx->scene_smem = rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris) <= RVPT_SMEM_SCENE_LIMIT;
 
     int occ_f = 0, occ_p = 0, occ_b = 0;
     if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
-    CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes));
+    CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes, L.n_nodes, L.n_tris));
     if (occ_f < 1 || occ_p < 1 || occ_b < 1)
         return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)", occ_f,
                     occ_p, occ_b);

@@ -32,8 +32,6 @@ namespace
 
 constexpr int kThreads = 256;      /* one reference workgroup worth of pixels */
 constexpr int kWarpsPerCta = kThreads / 32;
-constexpr uint32_t kChunkGrain = 4; /* 32-pixel chunks a warp claims per atomic */
-constexpr uint32_t kRayGrain = 4;   /* 32-ray groups a warp claims per atomic */
 
 #define RV_INF __int_as_float(0x7f800000)
 
@@ -113,6 +111,12 @@ struct SceneView
     const float4* tris;  /* 4 per triangle */
     const uint32_t* meta;
     const float4* mats;  /* 3 per material */
+    /* primary-wave copies relative to the shared camera origin (kRel only):
+     * node bounds minus origin, and dot(v0 - origin, n) per triangle — the
+     * first operations of intersect_aabb / intersect_triangle_fast, which are
+     * identical for every primary ray of a pinhole or spherical camera. */
+    const float4* rel_nodes;
+    const float* rel_num;
 };
 
 __device__ __forceinline__ SceneView make_view(const unsigned char* base, const SceneLayout& L)
@@ -122,14 +126,18 @@ __device__ __forceinline__ SceneView make_view(const unsigned char* base, const 
     v.tris = reinterpret_cast<const float4*>(base + L.off_tris);
     v.meta = reinterpret_cast<const uint32_t*>(base + L.off_meta);
     v.mats = reinterpret_cast<const float4*>(base + L.off_mats);
+    v.rel_nodes = nullptr;
+    v.rel_num = nullptr;
     return v;
 }
 
 /* ---- nearest hit: stackless walk in the reference's visiting order ------- */
 
+template <bool kRel>
 __device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f3 d, float& best_t,
                                               uint32_t& best_tri)
 {
+    const float4* __restrict__ nodes = kRel ? sc.rel_nodes : sc.nodes;
     /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
     const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
     best_t = RV_INF;
@@ -137,11 +145,21 @@ __device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
-        const float4 n0 = sc.nodes[2 * node];
-        const float4 n1 = sc.nodes[2 * node + 1];
-        const float fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
-        const float fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
-        const float fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
+        const float4 n0 = nodes[2 * node];
+        const float4 n1 = nodes[2 * node + 1];
+        float fx, nx, fy, ny, fz, nz;
+        if (kRel)
+        {
+            fx = n0.y * ix, nx = n0.x * ix;
+            fy = n0.w * iy, ny = n0.z * iy;
+            fz = n1.y * iz, nz = n1.x * iz;
+        }
+        else
+        {
+            fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
+            fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
+            fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
+        }
         float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
         float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
         t0 = fmaxf(t0, 0.0f);
@@ -162,8 +180,9 @@ __device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f
                     const float4 A = sc.tris[4 * i + 0];
                     const float4 B = sc.tris[4 * i + 1];
                     m = sc.meta[i];
-                    const float num = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
-                                             rv_make(B.x, B.y, B.z));
+                    const float num = kRel ? sc.rel_num[i]
+                                           : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
+                                                    rv_make(B.x, B.y, B.z));
                     const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
                     const float t = num / den;
                     if (0.0f < t && t < best_t)
@@ -212,6 +231,18 @@ __device__ __forceinline__ void slot_to_xy(const FrameParams& p, uint32_t slot, 
 
 /* ---- sample termination: compute_pass.comp:146-148, 157-166 --------------- */
 
+/* The previous running mean of a pixel is prefetched towards L1 when its path
+ * starts, so the dependent load in finish_sample does not pay the full HBM/L2
+ * latency at the end of the traversal (costs no registers). */
+__device__ __forceinline__ void prefetch_prev(const FrameParams& p, uint32_t slot)
+{
+    if (p.pass != p.aa - 1) return; /* accum is only read by the last pass of a frame */
+    const void* a = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8)
+                        ? static_cast<const void*>(p.accum_u8 + slot)
+                        : static_cast<const void*>(p.accum_f32 + slot);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+}
+
 __device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slot, rv_f3 s,
                                               uint32_t rng)
 {
@@ -229,7 +260,9 @@ __device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slo
         p.carry[slot] = make_float4(sum.x, sum.y, sum.z, __uint_as_float(rng));
         return;
     }
-    const rv_f3 sampled = rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f);
+    /* sampled /= aa ; x / 1.0f == x exactly, so the common aa = 1 case skips three divisions */
+    const rv_f3 sampled =
+        p.aa == 1 ? sum : rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f);
 
     rv_f3 prev;
     const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
@@ -274,11 +307,12 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
+template <bool kRel>
 __device__ __forceinline__ bool kajiya_step(const SceneView& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
-    trace_nearest(sc, s.o, s.d, t, tri);
+    trace_nearest<kRel>(sc, s.o, s.d, t, tri);
 
     if (tri == 0xFFFFFFFFu)
     {
@@ -465,62 +499,65 @@ __device__ __forceinline__ void clear_next_counters(const FrameParams& p)
 }
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
+template <bool kRel>
 __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneView& sc)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long traced = 0;
 
+    /* each warp owns one 32-pixel chunk at a time; the claim of the next chunk
+     * is issued before the current one is traced so the atomic's round trip to
+     * L2 is never on the critical path */
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr, 1u);
     for (;;)
     {
-        uint32_t c0 = 0;
-        if (lane == 0) c0 = atomicAdd(&wc.chunk_ctr, kChunkGrain);
-        c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
-        if (c0 >= p.n_chunks) break;
-        const uint32_t c1 = min(c0 + kChunkGrain, p.n_chunks);
-        for (uint32_t c = c0; c < c1; ++c)
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, claim, 0);
+        if (c >= p.n_chunks) break;
+        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr, 1u);
+
+        const uint32_t slot = c * 32u + lane;
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
+                            ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
+        bool alive = false;
+        PathState s;
+        if (inside)
         {
-            const uint32_t slot = c * 32u + lane;
-            uint32_t x, y;
-            slot_to_xy(p, slot, x, y);
-            const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
-                                ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
-            bool alive = false;
-            PathState s;
-            if (inside)
-            {
-                /* util.glsl:35-36; later samples of the frame continue the stream */
-                if (p.pass == 0)
-                    s.rng = rv_wang_hash(x + y * p.W) + p.frame;
-                else
-                    s.rng = __float_as_uint(p.carry[slot].w);
+            prefetch_prev(p, slot);
+            /* util.glsl:35-36; later samples of the frame continue the stream */
+            if (p.pass == 0)
+                s.rng = rv_wang_hash(x + y * p.W) + p.frame;
+            else
+                s.rng = __float_as_uint(p.carry[slot].w);
 
-                /* compute_pass.comp:153-154 */
-                const float jx = rv_rand(&s.rng);
-                const float jy = rv_rand(&s.rng);
-                const float cx = ((float)x + jx) * p.inv_dim_x;
-                float cy = ((float)y + jy) * p.inv_dim_y;
-                cy = 1.0f - cy;
-                camera_ray(p, cx, cy, s.o, s.d);
-                s.thr = rv_make(1.0f, 1.0f, 1.0f);
-                s.col = rv_make(0.0f, 0.0f, 0.0f);
+            /* compute_pass.comp:153-154 */
+            const float jx = rv_rand(&s.rng);
+            const float jy = rv_rand(&s.rng);
+            const float cx = ((float)x + jx) * p.inv_dim_x;
+            float cy = ((float)y + jy) * p.inv_dim_y;
+            cy = 1.0f - cy;
+            camera_ray(p, cx, cy, s.o, s.d);
+            s.thr = rv_make(1.0f, 1.0f, 1.0f);
+            s.col = rv_make(0.0f, 0.0f, 0.0f);
 
-                rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
-                if (p.max_bounces > 0)
-                {
-                    alive = kajiya_step(sc, s, sample);
-                    if (alive && p.max_bounces == 1)
-                    {
-                        alive = false; /* :674-675 ran out of iterations */
-                        sample = rv_make(0.0f, 0.0f, 0.0f);
-                    }
-                }
-                if (!alive) finish_sample(p, slot, sample, s.rng);
-            }
+            rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
             if (p.max_bounces > 0)
-                traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
-            push_survivors(p, p.queue[0], &wc.qcount[0], alive, slot, s);
+            {
+                alive = kajiya_step<kRel>(sc, s, sample);
+                if (alive && p.max_bounces == 1)
+                {
+                    alive = false; /* :674-675 ran out of iterations */
+                    sample = rv_make(0.0f, 0.0f, 0.0f);
+                }
+            }
+            if (!alive) finish_sample(p, slot, sample, s.rng);
         }
+        if (p.max_bounces > 0)
+            traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
+        push_survivors(p, p.queue[0], &wc.qcount[0], alive, slot, s);
     }
     if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
 }
@@ -540,83 +577,91 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
     s.col = rv_make(a3.x, a3.y, a3.z);
 }
 
-/* iteration b >= 1 over queue[(b-1)&1] -> queue[b&1]; `r0` is the first ray
- * group this warp already owns (claimed by its CTA), later ones are claimed
- * per warp. */
+/* Iteration b >= 1 of the bounce loop over queue[(b-1)&1] -> queue[b&1].
+ *
+ * How the wave's rays are dealt to warps depends on its size (all warp-uniform):
+ *   dynamic   big waves: warps claim 32-ray groups from an atomic counter
+ *             (`first` = a group the warp already owns, or >= count for none;
+ *             claimed groups start at `claim_offset` + the counter value);
+ *   spread    waves that cannot fill the machine twice over: every warp takes
+ *             the same share, L = ceil(count / n_warps) <= 32 lanes at a time,
+ *             so a small incoherent wave costs one short batch per warp instead
+ *             of a few warps grinding through 32-wide divergent batches;
+ *   in_thread (with spread, L <= 2) the paths run to their end inside their
+ *             threads instead of going back through the queue; rays of the
+ *             later bounces are counted as they are traced.
+ */
+#define RVPT_WAVE_SPREAD 1u
+#define RVPT_WAVE_IN_THREAD 2u
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneView& sc, int b,
-                                             uint32_t count, uint32_t r0)
+                                             uint32_t count, uint32_t mode, uint32_t first,
+                                             uint32_t claim_offset)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const PathQueue qin = p.queue[(b - 1) & 1];
     const PathQueue qout = p.queue[b & 1];
     const uint32_t lane = threadIdx.x & 31u;
-    const bool last_bounce = (b == p.max_bounces - 1);
-    for (;;)
+    unsigned long long* active = p.ctr->stats[p.stats_set].active;
+    const bool spread = (mode & RVPT_WAVE_SPREAD) != 0;
+    const bool in_thread = (mode & RVPT_WAVE_IN_THREAD) != 0;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t L = spread ? min(32u, (count + n_warps - 1) / n_warps) : 32u;
+
+    uint32_t claim = first;
+    uint32_t base = spread ? gwarp * L : first;
+    if (!spread && lane == 0 && first < count)
+        claim = atomicAdd(&wc.work_ctr[b], 32u) + claim_offset;
+    for (uint32_t round = 0;; ++round)
     {
-        if (r0 >= count) break;
-        const uint32_t r1 = min(r0 + 32u * kRayGrain, count);
-        for (uint32_t base = r0; base < r1; base += 32u)
+        if (spread)
         {
-            const uint32_t i = base + lane;
-            bool alive = false;
-            PathState s;
-            uint32_t slot = 0;
-            if (i < count)
+            if ((uint64_t)round * n_warps * L >= count) break;
+            base = (round * n_warps + gwarp) * L;
+        }
+        else if (base >= count)
+            break;
+
+        const uint32_t i = base + lane;
+        bool alive = false;
+        PathState s;
+        uint32_t slot = 0;
+        if (lane < L && i < count)
+        {
+            load_path(qin, i, s, slot);
+            prefetch_prev(p, slot);
+            rv_f3 sample;
+            for (int k = b;; ++k)
             {
-                load_path(qin, i, s, slot);
-                rv_f3 sample;
-                alive = kajiya_step(sc, s, sample);
-                if (alive && last_bounce)
+                alive = kajiya_step<false>(sc, s, sample);
+                if (alive && k == p.max_bounces - 1)
                 {
                     alive = false; /* integrators.glsl:674-675: col is discarded */
                     sample = rv_make(0.0f, 0.0f, 0.0f);
                 }
-                if (!alive) finish_sample(p, slot, sample, s.rng);
+                if (!in_thread || !alive) break;
+                if (k + 1 < RVPT_MAX_BOUNCE_STATS) atomicAdd(&active[k + 1], 1ull);
             }
-            push_survivors(p, qout, &wc.qcount[b], alive, slot, s);
+            if (!alive) finish_sample(p, slot, sample, s.rng);
         }
-        uint32_t nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&wc.work_ctr[b], 32u * kRayGrain);
-        r0 = __shfl_sync(0xFFFFFFFFu, nxt, 0);
-    }
-}
+        if (!in_thread) push_survivors(p, qout, &wc.qcount[b], alive, slot, s);
 
-/* A wave too small to fill the machine: ray i goes to warp (i % n_warps),
- * lane (i / n_warps), so the few rays sit alone in their warps (no divergence
- * serialisation) and every path runs to its end inside its thread. Counts the
- * rays of the later bounces as it goes. */
-__device__ __forceinline__ void tail_phase(const FrameParams& p, const SceneView& sc, int b,
-                                           uint32_t count)
-{
-    const PathQueue qin = p.queue[(b - 1) & 1];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t i = lane * n_warps + gwarp;
-    if (i >= count) return;
-    PathState s;
-    uint32_t slot;
-    load_path(qin, i, s, slot);
-    rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
-    unsigned long long* active = p.ctr->stats[p.stats_set].active;
-    for (int k = b; k < p.max_bounces; ++k)
-    {
-        if (k > b && k < RVPT_MAX_BOUNCE_STATS) atomicAdd(&active[k], 1ull);
-        if (!kajiya_step(sc, s, sample)) break;
-        sample = rv_make(0.0f, 0.0f, 0.0f); /* still alive: black if the loop ends here */
+        if (!spread)
+        {
+            base = __shfl_sync(0xFFFFFFFFu, claim, 0);
+            if (lane == 0 && base < count) claim = atomicAdd(&wc.work_ctr[b], 32u) + claim_offset;
+        }
     }
-    finish_sample(p, slot, sample, s.rng);
 }
 
 /* ======================================================================== */
 /* k_frame: the whole frame (one aa pass) in ONE persistent cooperative launch */
 /* ======================================================================== */
-template <bool kSmem>
+template <bool kSmem, bool kRel>
 __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    __shared__ uint32_t first_claim;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 
     clear_next_counters(p);
@@ -625,11 +670,34 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
     {
         stage_scene(smem, &bar, p.scene, p.layout.bytes);
         sc = make_view(smem, p.layout);
+        if (kRel)
+        {
+            /* origin-relative copies for the primary wave (same subtractions /
+             * dot product every primary ray would do: cam.matrix[3].xyz is the
+             * origin of all pinhole and spherical camera rays, camera.glsl:46,94) */
+            float4* rel_nodes = reinterpret_cast<float4*>(smem + p.layout.bytes);
+            float* rel_num = reinterpret_cast<float*>(rel_nodes + 2 * p.layout.n_nodes);
+            const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
+            for (uint32_t i = threadIdx.x; i < p.layout.n_nodes; i += blockDim.x)
+            {
+                const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+                rel_nodes[2 * i] = make_float4(n0.x - o.x, n0.y - o.x, n0.z - o.y, n0.w - o.y);
+                rel_nodes[2 * i + 1] = make_float4(n1.x - o.z, n1.y - o.z, n1.z, n1.w);
+            }
+            for (uint32_t i = threadIdx.x; i < p.layout.n_tris; i += blockDim.x)
+            {
+                const float4 A = sc.tris[4 * i], B = sc.tris[4 * i + 1];
+                rel_num[i] = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
+            }
+            sc.rel_nodes = rel_nodes;
+            sc.rel_num = rel_num;
+            __syncthreads();
+        }
     }
     else
         sc = make_view(p.scene, p.layout);
 
-    primary_phase(p, sc);
+    primary_phase<kRel>(p, sc);
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     for (int b = 1; b < p.max_bounces; ++b)
@@ -639,17 +707,21 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
         if (count == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
             atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
+        const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         if (count <= p.tail_threshold)
         {
-            tail_phase(p, sc, b, count);
+            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD, 0, 0);
             break;
         }
-        if (threadIdx.x == 0)
-            first_claim = atomicAdd(&wc.work_ctr[b], 32u * kRayGrain * kWarpsPerCta);
-        __syncthreads();
-        const uint32_t cta_first = first_claim;
-        __syncthreads(); /* first_claim is rewritten next wave */
-        bounce_phase(p, sc, b, count, cta_first + (threadIdx.x >> 5) * 32u * kRayGrain);
+        if (count <= 64u * n_warps)
+        {
+            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD, 0, 0);
+            continue;
+        }
+        /* every warp starts with its own 32-ray group; the rest is claimed dynamically
+         * from the counter, which therefore starts behind those n_warps groups */
+        const uint32_t gwarp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        bounce_phase(p, sc, b, count, 0u, gwarp * 32u, 32u * n_warps);
     }
 }
 
@@ -670,7 +742,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     }
     else
         sc = make_view(p.scene, p.layout);
-    primary_phase(p, sc);
+    primary_phase<false>(p, sc);
 }
 
 template <bool kSmem>
@@ -684,7 +756,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     const uint32_t count = wc.qcount[b - 1];
     /* an empty wave costs one atomic per CTA and no scene staging */
     if (threadIdx.x == 0)
-        first_claim = count ? atomicAdd(&wc.work_ctr[b], 32u * kRayGrain * kWarpsPerCta) : count;
+        first_claim = count ? atomicAdd(&wc.work_ctr[b], 32u * kWarpsPerCta) : count;
     __syncthreads();
     const uint32_t cta_first = first_claim;
     if (cta_first >= count) return;
@@ -700,7 +772,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     }
     else
         sc = make_view(p.scene, p.layout);
-    bounce_phase(p, sc, b, count, cta_first + (threadIdx.x >> 5) * 32u * kRayGrain);
+    bounce_phase(p, sc, b, count, 0u, cta_first + (threadIdx.x >> 5) * 32u, 0u);
 }
 
 /* ======================================================================== */
@@ -830,7 +902,10 @@ static size_t smem_bytes_for(const FrameParams& p, bool smem) { return smem ? p.
 cudaError_t configure_kernels(size_t max_dynamic_smem)
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_frame<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_frame<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)max_dynamic_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_frame<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)max_dynamic_smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -841,15 +916,21 @@ cudaError_t configure_kernels(size_t max_dynamic_smem)
     return e;
 }
 
+size_t frame_smem_bytes(size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris)
+{
+    /* blob + origin-relative node copy + one float per triangle */
+    return scene_bytes + (size_t)n_nodes * 32u + (((size_t)n_tris * 4u + 15u) & ~(size_t)15u);
+}
+
 cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bounce_ctas_per_sm,
-                      bool smem, size_t scene_bytes)
+                      bool smem, size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris)
 {
     const size_t dyn = smem ? scene_bytes : 0;
     cudaError_t e;
     if (smem)
     {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<true>, kThreads,
-                                                          dyn);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<true, true>,
+                                                          kThreads, frame_smem_bytes(scene_bytes, n_nodes, n_tris));
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<true>,
                                                           kThreads, dyn);
@@ -859,7 +940,7 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
     }
     else
     {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<false>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<false, false>,
                                                           kThreads, dyn);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<false>,
@@ -875,10 +956,17 @@ cudaError_t launch_frame(const FrameParams& p, bool smem, int grid, cudaStream_t
 {
     void* args[] = {const_cast<FrameParams*>(&p)};
     if (smem)
-        return cudaLaunchCooperativeKernel((const void*)k_frame<true>, dim3(grid), dim3(kThreads),
-                                           args, smem_bytes_for(p, true), st);
-    return cudaLaunchCooperativeKernel((const void*)k_frame<false>, dim3(grid), dim3(kThreads), args,
-                                       0, st);
+    {
+        const size_t dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris);
+        /* the ortho camera has a different origin per ray: no shared-origin copies */
+        if (p.camera_mode != 1)
+            return cudaLaunchCooperativeKernel((const void*)k_frame<true, true>, dim3(grid),
+                                               dim3(kThreads), args, dyn, st);
+        return cudaLaunchCooperativeKernel((const void*)k_frame<true, false>, dim3(grid),
+                                           dim3(kThreads), args, dyn, st);
+    }
+    return cudaLaunchCooperativeKernel((const void*)k_frame<false, false>, dim3(grid),
+                                       dim3(kThreads), args, 0, st);
 }
 
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)
