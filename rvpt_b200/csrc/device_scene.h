@@ -94,10 +94,12 @@ struct PathQueue
  * first pass of frame F zeroes the stats set of frame F+1 (whose previous user,
  * launch L-1 / frame F-1, has completed in stream order).
  */
+#define RVPT_CHUNK_SHARDS 16u
 struct WaveCounters
 {
-    uint32_t chunk_ctr;    /* primary phase work distribution */
-    uint32_t pad0[3];
+    /* primary phase work distribution: one counter per shard, 128 B apart so the
+     * shards live in different L2 atomic units; shard k hands out chunks k, k+16, ... */
+    uint32_t chunk_ctr[RVPT_CHUNK_SHARDS * 32u];
     uint32_t work_ctr[64]; /* bounce phase work distribution, per bounce */
     uint32_t qcount[64];   /* survivors pushed by bounce b (read by b+1) */
 };

@@ -32,6 +32,10 @@ namespace
 
 constexpr int kThreads = 256;      /* one reference workgroup worth of pixels */
 constexpr int kWarpsPerCta = kThreads / 32;
+#ifndef RVPT_CHUNK_GRAIN
+#define RVPT_CHUNK_GRAIN 1
+#endif
+constexpr uint32_t kChunkGrain = RVPT_CHUNK_GRAIN; /* 32-pixel chunks per claim */
 
 #define RV_INF __int_as_float(0x7f800000)
 
@@ -506,17 +510,46 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long traced = 0;
 
-    /* each warp owns one 32-pixel chunk at a time; the claim of the next chunk
-     * is issued before the current one is traced so the atomic's round trip to
-     * L2 is never on the critical path */
+    /* Work distribution: every warp claims one 32-pixel chunk at a time, so sky
+     * and geometry balance at the finest grain. One atomic counter cannot hand
+     * out 65 k chunks per frame — the L2 atomic unit retires roughly one
+     * same-address atomic per 1.5 SM cycles, as long as the whole frame — so the
+     * counter is sharded 16 ways (different cache lines, different L2 slices):
+     * shard k hands out claims k, k+16, ... of kChunkGrain chunks; a warp starts on shard (warp % 16)
+     * and moves to the next shard when its own runs dry (built-in work
+     * stealing). The claim for the next chunk is issued before the current one
+     * is traced, so its round trip to L2 is off the critical path. */
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_units = (p.n_chunks + kChunkGrain - 1) / kChunkGrain; /* claims are kChunkGrain chunks */
+    uint32_t shard = gwarp % RVPT_CHUNK_SHARDS;
+    uint32_t dry = 0; /* shards found exhausted */
     uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr, 1u);
+    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
     for (;;)
     {
-        const uint32_t c = __shfl_sync(0xFFFFFFFFu, claim, 0);
-        if (c >= p.n_chunks) break;
-        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr, 1u);
+        uint32_t unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+        while (unit >= n_units)
+        {
+            /* this shard is dry: look at all 16 counters with one parallel load and
+             * move to the next shard that still has work (or stop if none has) */
+            uint32_t v = 0xFFFFFFFFu;
+            if (lane < RVPT_CHUNK_SHARDS)
+                v = *reinterpret_cast<volatile uint32_t*>(&wc.chunk_ctr[lane * 32u]);
+            const bool has_work = lane < RVPT_CHUNK_SHARDS &&
+                                  (uint64_t)v * RVPT_CHUNK_SHARDS + lane < n_units;
+            uint32_t live = __ballot_sync(0xFFFFFFFFu, has_work);
+            if (live == 0) { dry = RVPT_CHUNK_SHARDS; break; }
+            /* first live shard after the current one, cyclically */
+            const uint32_t rot = (live >> (shard + 1u)) | (live << (RVPT_CHUNK_SHARDS - 1u - shard));
+            shard = (shard + 1u + (uint32_t)(__ffs(rot & 0xFFFFu) - 1)) % RVPT_CHUNK_SHARDS;
+            if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
+            unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+        }
+        if (unit >= n_units) break;
+        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
 
+      for (uint32_t c = unit * kChunkGrain, c_end = min(c + kChunkGrain, p.n_chunks); c < c_end; ++c)
+      {
         const uint32_t slot = c * 32u + lane;
         uint32_t x, y;
         slot_to_xy(p, slot, x, y);
@@ -558,6 +591,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
         if (p.max_bounces > 0)
             traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
         push_survivors(p, p.queue[0], &wc.qcount[0], alive, slot, s);
+      }
     }
     if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
 }
@@ -580,9 +614,8 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
 /* Iteration b >= 1 of the bounce loop over queue[(b-1)&1] -> queue[b&1].
  *
  * How the wave's rays are dealt to warps depends on its size (all warp-uniform):
- *   dynamic   big waves: warps claim 32-ray groups from an atomic counter
- *             (`first` = a group the warp already owns, or >= count for none;
- *             claimed groups start at `claim_offset` + the counter value);
+ *   dynamic   big waves: full 32-ray groups, mostly dealt statically, the last
+ *             eighth claimed from an atomic counter;
  *   spread    waves that cannot fill the machine twice over: every warp takes
  *             the same share, L = ceil(count / n_warps) <= 32 lanes at a time,
  *             so a small incoherent wave costs one short batch per warp instead
@@ -594,8 +627,7 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_IN_THREAD 2u
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneView& sc, int b,
-                                             uint32_t count, uint32_t mode, uint32_t first,
-                                             uint32_t claim_offset)
+                                             uint32_t count, uint32_t mode)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const PathQueue qin = p.queue[(b - 1) & 1];
@@ -606,23 +638,35 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     const bool in_thread = (mode & RVPT_WAVE_IN_THREAD) != 0;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    /* spread: L lanes per warp and round; otherwise full 32-ray groups, 7/8 of
+     * each warp's share dealt statically and the rest claimed from the counter
+     * (same reasoning as in primary_phase) */
     const uint32_t L = spread ? min(32u, (count + n_warps - 1) / n_warps) : 32u;
+    const uint32_t groups = (count + L - 1) / L;
+    const uint32_t per_warp = groups / n_warps;
+    const uint32_t static_rounds = spread ? (groups + n_warps - 1) / n_warps : per_warp - (per_warp >> 3);
+    const uint32_t dyn_base = static_rounds * n_warps;
 
-    uint32_t claim = first;
-    uint32_t base = spread ? gwarp * L : first;
-    if (!spread && lane == 0 && first < count)
-        claim = atomicAdd(&wc.work_ctr[b], 32u) + claim_offset;
+    uint32_t claim = 0;
+    if (static_rounds == 0 && lane == 0) claim = atomicAdd(&wc.work_ctr[b], 1u);
     for (uint32_t round = 0;; ++round)
     {
-        if (spread)
-        {
-            if ((uint64_t)round * n_warps * L >= count) break;
-            base = (round * n_warps + gwarp) * L;
-        }
-        else if (base >= count)
+        uint32_t g;
+        if (round < static_rounds)
+            g = round * n_warps + gwarp;
+        else if (spread)
             break;
+        else
+            g = dyn_base + __shfl_sync(0xFFFFFFFFu, claim, 0);
+        if (g >= groups)
+        {
+            if (spread) continue; /* other warps of this round still have rays; warp-uniform */
+            break;
+        }
+        if (!spread && round + 1 >= static_rounds && lane == 0)
+            claim = atomicAdd(&wc.work_ctr[b], 1u);
 
-        const uint32_t i = base + lane;
+        const uint32_t i = g * L + lane;
         bool alive = false;
         PathState s;
         uint32_t slot = 0;
@@ -645,12 +689,6 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             if (!alive) finish_sample(p, slot, sample, s.rng);
         }
         if (!in_thread) push_survivors(p, qout, &wc.qcount[b], alive, slot, s);
-
-        if (!spread)
-        {
-            base = __shfl_sync(0xFFFFFFFFu, claim, 0);
-            if (lane == 0 && base < count) claim = atomicAdd(&wc.work_ctr[b], 32u) + claim_offset;
-        }
     }
 }
 
@@ -710,18 +748,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         if (count <= p.tail_threshold)
         {
-            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD, 0, 0);
+            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
             break;
         }
-        if (count <= 64u * n_warps)
-        {
-            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD, 0, 0);
-            continue;
-        }
-        /* every warp starts with its own 32-ray group; the rest is claimed dynamically
-         * from the counter, which therefore starts behind those n_warps groups */
-        const uint32_t gwarp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-        bounce_phase(p, sc, b, count, 0u, gwarp * 32u, 32u * n_warps);
+        bounce_phase(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
     }
 }
 
@@ -750,18 +780,11 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    __shared__ uint32_t first_claim;
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const uint32_t count = wc.qcount[b - 1];
-    /* an empty wave costs one atomic per CTA and no scene staging */
-    if (threadIdx.x == 0)
-        first_claim = count ? atomicAdd(&wc.work_ctr[b], 32u * kWarpsPerCta) : count;
-    __syncthreads();
-    const uint32_t cta_first = first_claim;
-    if (cta_first >= count) return;
-    /* exactly one CTA claims offset 0: it records the wave size */
-    if (threadIdx.x == 0 && cta_first == 0 && b < RVPT_MAX_BOUNCE_STATS)
+    if (count == 0) return; /* an empty wave costs nothing but the launch */
+    if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
         atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
 
     SceneView sc;
@@ -772,7 +795,8 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     }
     else
         sc = make_view(p.scene, p.layout);
-    bounce_phase(p, sc, b, count, 0u, cta_first + (threadIdx.x >> 5) * 32u, 0u);
+    const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+    bounce_phase(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
 }
 
 /* ======================================================================== */
