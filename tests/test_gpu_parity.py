@@ -135,6 +135,30 @@ def test_brute_force_flag_and_internal_bvh(rv, oracle_mod, builtin):
     _assert_bit_equal(eng_int.read_accum_f32(), eng_bvh.read_accum_f32(), "internal BVH")
 
 
+def test_gpu_matches_committed_golden_pins(rv, oracle_mod, builtin, cornell):
+    """File-based target: the sha256 pins under tests/golden/ (written by
+    tests/golden/make_golden.py from the oracle) — BASELINE configs 1-3 shapes."""
+    import hashlib
+    import json
+    from pathlib import Path
+    from golden.make_golden import CASES
+    pins = json.loads((Path(__file__).parent / "golden" / "oracle_pins.json").read_text())
+    scenes = {"builtin": builtin, "cornell": cornell}
+    for name, (scene, W, H, pose, fov, frames, over, flags) in CASES.items():
+        prep = scenes[scene]
+        cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+        eng = rv.Engine(W, H, flags=flags)
+        eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+        for f in range(frames):
+            eng.render_frame(rv.default_settings(frame=f, **over), cam)
+        acc = eng.read_accum_f32()
+        assert hashlib.sha256(acc.tobytes()).hexdigest() == pins[name]["accum_sha256"], name
+        assert hashlib.sha256(eng.read_output_rgba8().tobytes()).hexdigest() == \
+            pins[name]["rgba8_sha256"], name
+        assert eng.stats()["active"] == pins[name]["active"], name
+        eng.close()
+
+
 def test_unfused_waves_equal_fused_frame_kernel(rv, oracle_mod, cornell):
     """One launch per wave (UNFUSED) and the persistent cooperative k_frame are
     the same computation."""
