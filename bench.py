@@ -50,7 +50,7 @@ UNIT = "Msamples/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
@@ -60,9 +60,13 @@ def parse_args():
     ap.add_argument("--aa", type=int, default=1)
     ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell"])
     ap.add_argument("--pose", default="default", choices=["default", "pinned"])
-    ap.add_argument("--gather", default="rgba8", choices=["rgba8", "none"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="N>1: p2p = kernels store pixels into rank 0's image over NVLink (fused); "
+                         "nccl = one all_gather_into_tensor per frame + untile")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay each step from a CUDA graph (captured through the C ABI)")
     return ap.parse_args()
 
 
@@ -99,7 +103,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
+                 "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -234,26 +238,44 @@ def run_ours(args):
     settings_ptr = [s.ctypes.data for s in settings]
     cam_ptr = cam.ctypes.data
 
-    # multi-GPU: kernels write rgba8 tiles straight into this rank's slot of the gather buffer
-    gathered = raster = None
-    gather = world > 1 and args.gather == "rgba8"
-    if world > 1:
-        ti = eng.tile_info()
-        slot_elems = ti.n_local_tiles_padded * 256
-        gathered = torch.zeros(world * slot_elems, dtype=torch.int32, device="cuda")
-        raster = torch.zeros(H * W, dtype=torch.int32, device="cuda")
-        my_slot = gathered[rank * slot_elems:(rank + 1) * slot_elems]
-        eng.set_external_tiles(None, my_slot.data_ptr())
+    # multi-GPU assembly of the image on rank 0:
+    #   p2p   every rank's kernels store finished rgba8 pixels straight into rank 0's raster
+    #         image over NVLink (CUDA IPC peer mapping) — the gather is fused into the frame
+    #         kernel, nothing else runs per frame;
+    #   nccl  the kernels write tiles into the rank's slot of a gather buffer, ONE
+    #         all_gather_into_tensor per frame, rank 0 untiles.
+    fg = po = None
+    gather = args.gather if world > 1 else "none"
+    if gather == "nccl":
+        from rvpt_b200.distributed import FrameGather
+        fg = FrameGather(eng, dist, torch, torch.device("cuda", local_rank))
+    elif gather == "p2p":
+        from rvpt_b200.distributed import PeerOutput
+        po = PeerOutput(eng, dist, torch, torch.device("cuda", local_rank))
 
     def frames_of_step():
         for f in range(F):
+            if fg:
+                fg.begin_frame()          # device-side wait for the buffer's previous gather
             eng.render_frame_raw(settings_ptr[f], cam_ptr)
-            if gather:
-                dist.all_gather_into_tensor(gathered, my_slot)
-                if rank == 0:
-                    eng.untile(gathered.data_ptr(), raster.data_ptr(), 4)
+            if fg:
+                fg.end_frame()            # async all-gather + untile
+        if fg:
+            fg.flush()                    # the step ends when its last image is assembled
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # 2x L2
+
+    # One step = F frame launches (+ F gathers). Captured once into a CUDA graph through
+    # the very same C-ABI calls and replayed: the host submits one graph per step
+    # instead of F cooperative launches + F collectives.
+    step_graph = None
+    graph_note = "off"
+
+    def run_step():
+        if step_graph is not None:
+            step_graph.replay()
+        else:
+            frames_of_step()
 
     def barrier():
         if world > 1:
@@ -264,6 +286,25 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         frames_of_step()
     barrier()
+    if args.graph != "off" and gather != "nccl":  # NCCL capture + side streams: not replay-safe here
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                frames_of_step()
+            step_graph, graph_note = g, "one CUDA graph per step (captured through the C ABI)"
+        except Exception as exc:  # noqa: BLE001
+            if args.graph == "on":
+                raise
+            graph_note = f"capture failed ({type(exc).__name__}): direct launches"
+            torch.cuda.synchronize()
+        ok = torch.tensor([1 if step_graph is not None else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            step_graph = None
+        for _ in range(2):
+            run_step()
+        barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -275,7 +316,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         starts[k].record(stream)
-        frames_of_step()
+        run_step()
         ends[k].record(stream)
     barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
@@ -284,7 +325,7 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     st = eng.stats()
-    launches_per_frame = st["kernel_launches"] + (1 if (gather and rank == 0) else 0)
+    launches_per_frame = st["kernel_launches"] + (1 if (fg and rank == 0) else 0)
     clocks = sampler.stop() if rank == 0 else None
 
     samples_per_step = W * H * args.aa * F
@@ -344,11 +385,17 @@ def run_ours(args):
         frames_of_step()
         if world == 1:
             eng.read_output_rgba8(out_np)              # device -> pinned host, synchronises
-        else:
+        elif po:
+            po.finish()                                # all ranks' pixels are in rank 0's image
             if rank == 0:
-                out_pinned.view(torch.int32).view(-1).copy_(raster, non_blocking=False)
+                eng.read_output_rgba8(out_np)
+        elif fg:
+            if rank == 0:
+                out_pinned.view(torch.int32).view(-1).copy_(fg.raster, non_blocking=False)
             else:
                 torch.cuda.synchronize()
+        else:
+            torch.cuda.synchronize()
 
     for _ in range(3):
         e2e_step()
@@ -377,8 +424,12 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": name, "frames_per_step": F, "samples_per_step": samples_per_step,
                        "partition": f"16x16 tiles, tile_id % {world} == rank" if world > 1 else "none",
-                       "gather": ("rgba8 all_gather_into_tensor per frame + untile on rank 0"
-                                  if gather else "none"),
+                       "gather": {"p2p": "fused: kernels store rgba8 pixels into rank 0's raster image "
+                                         "over NVLink peer memory (CUDA IPC); barrier per step",
+                                  "nccl": "rgba8 all_gather_into_tensor per frame (async, double-"
+                                          "buffered) + untile on rank 0",
+                                  "none": "none"}[gather],
+                       "launch": graph_note,
                        "l2": "256 MiB memset between steps (outside the timed events); "
                              "frames inside a step share L2 as in the real render loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,

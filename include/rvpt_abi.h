@@ -237,7 +237,10 @@ RVPT_API int rvpt_b200_get_tile_info(rvpt_b200_ctx* ctx, rvpt_b200_tile_info* ou
 /* Redirect the per-tile outputs into caller-owned device memory (e.g. this
  * rank's slot of an all-gather buffer) so the frame kernels write the gather
  * payload in place and no pack pass exists. Pass NULL to keep the current
- * buffer. Sizes as reported by rvpt_b200_get_tile_info(). */
+ * buffer. Sizes as reported by rvpt_b200_get_tile_info(). Takes effect for
+ * frames launched after the call and does not synchronise: the caller orders
+ * the reuse of a buffer against whatever still reads it (e.g. an in-flight
+ * gather) with stream/event dependencies. */
 RVPT_API int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_tiles,
                                           void* d_rgba8_tiles);
 
@@ -246,6 +249,28 @@ RVPT_API int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_tile
  * elem_bytes is 4 (rgba8) or 16 (float4). Runs on the ctx stream. */
 RVPT_API int rvpt_b200_untile(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
                               uint32_t elem_bytes, uint32_t nranks);
+/* Same, on an explicit CUDA stream (so the scatter can follow an asynchronous
+ * gather without blocking the render stream). */
+RVPT_API int rvpt_b200_untile_on(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
+                                 uint32_t elem_bytes, uint32_t nranks, void* cuda_stream);
+
+/* ------------------------------------------------------------------------ */
+/* Fused gather over NVLink peer memory. Instead of collecting tiles with a  */
+/* collective after the frame, the frame kernels of every rank store their    */
+/* finished rgba8 pixels straight into ONE raster image that lives on the    */
+/* display rank's GPU (peer-mapped through CUDA IPC): the "gather" is the     */
+/* kernels' own 32-byte row stores travelling over NVLink while they compute. */
+/* The display rank exports its image, the others attach to it; all a frame  */
+/* needs afterwards is stream completion on every rank + a barrier.          */
+/* ------------------------------------------------------------------------ */
+#define RVPT_B200_IPC_HANDLE_BYTES 64
+/* Display rank: returns the CUDA IPC handle of this ctx's raster result image
+ * (W*H*4 bytes), creating it if the ctx is partitioned; its own tiles are then
+ * written into it as well. */
+RVPT_API int rvpt_b200_export_output(rvpt_b200_ctx* ctx, unsigned char handle[64]);
+/* Other ranks (separate processes on the same node): map the display rank's
+ * image and write this rank's pixels into it. */
+RVPT_API int rvpt_b200_attach_output(rvpt_b200_ctx* ctx, const unsigned char handle[64]);
 
 /* ------------------------------------------------------------------------ */
 /* Host-side utilities (no GPU needed).                                      */

@@ -68,6 +68,10 @@ SIGNATURES = {
     "rvpt_b200_get_tile_info": (C.c_int, [C.c_void_p, C.POINTER(TileInfo)]),
     "rvpt_b200_set_external_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvpt_b200_untile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "rvpt_b200_untile_on": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                      C.c_void_p]),
+    "rvpt_b200_export_output": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvpt_b200_attach_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_build_bvh": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
                                       C.c_void_p]),
     "rvpt_b200_camera_data": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,

@@ -60,7 +60,8 @@ struct rvpt_b200_ctx
     void* d_out_tiles = nullptr;  /* own allocation */
     void* accum = nullptr;        /* in use (own or external) */
     void* out_tiles = nullptr;
-    uchar4* d_out_raster = nullptr; /* nranks == 1 */
+    uchar4* d_out_raster = nullptr; /* nranks == 1, or exported by the display rank */
+    uchar4* peer_out_raster = nullptr; /* display rank's image, mapped through CUDA IPC */
     float4* d_carry = nullptr;      /* allocated on first aa > 1 */
     PathQueue queue[2]{};
     FrameCounters* d_ctr = nullptr;
@@ -490,6 +491,7 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
     {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->peer_out_raster) cudaIpcCloseMemHandle(ctx->peer_out_raster);
         free_frame_buffers(ctx);
         cudaFree(ctx->d_scene);
         for (auto& t : ctx->timed) ctx->event_pool.push_back(t);
@@ -614,7 +616,8 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.accum_f32 = (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? nullptr : (float4*)ctx->accum;
     p.accum_u8 = (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? (uchar4*)ctx->accum : nullptr;
     p.out_tiles = (uchar4*)ctx->out_tiles;
-    p.out_raster = ctx->nranks == 1 ? ctx->d_out_raster : nullptr;
+    /* raster target: the display rank's image over NVLink, else our own */
+    p.out_raster = ctx->peer_out_raster ? ctx->peer_out_raster : ctx->d_out_raster;
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
 
@@ -674,7 +677,7 @@ extern "C" int rvpt_b200_read_output_rgba8(rvpt_b200_ctx* ctx, uint8_t* dst)
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)ctx->W * ctx->H * 4;
-    if (ctx->nranks == 1)
+    if (ctx->d_out_raster && !ctx->peer_out_raster)
     {
         CU(cudaMemcpyAsync(dst, ctx->d_out_raster, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -829,8 +832,6 @@ extern "C" int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_ti
     if (!ctx) return RVPT_B200_EINVAL;
     int rc = ensure_frame_buffers(ctx);
     if (rc) return rc;
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
     if (d_accum_tiles) ctx->accum = d_accum_tiles;
     if (d_rgba8_tiles) ctx->out_tiles = d_rgba8_tiles;
     return 0;
@@ -838,6 +839,13 @@ extern "C" int rvpt_b200_set_external_tiles(rvpt_b200_ctx* ctx, void* d_accum_ti
 
 extern "C" int rvpt_b200_untile(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
                                 uint32_t elem_bytes, uint32_t nranks)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    return rvpt_b200_untile_on(ctx, d_gathered, d_raster, elem_bytes, nranks, ctx->stream);
+}
+
+extern "C" int rvpt_b200_untile_on(rvpt_b200_ctx* ctx, const void* d_gathered, void* d_raster,
+                                   uint32_t elem_bytes, uint32_t nranks, void* cuda_stream)
 {
     if (!ctx || !d_gathered || !d_raster) return RVPT_B200_EINVAL;
     if (elem_bytes != 4 && elem_bytes != 16)
@@ -847,7 +855,39 @@ extern "C" int rvpt_b200_untile(rvpt_b200_ctx* ctx, const void* d_gathered, void
     CU(cudaSetDevice(ctx->device));
     CU(rvpt::launch_untile(d_gathered, d_raster, elem_bytes / 4, ctx->W, ctx->H, ctx->tiles_x,
                            ctx->n_tiles, ctx->nranks, 0, ctx->nranks, ctx->n_local_padded,
-                           ctx->stream));
+                           (cudaStream_t)cuda_stream));
+    return 0;
+}
+
+extern "C" int rvpt_b200_export_output(rvpt_b200_ctx* ctx, unsigned char handle[64])
+{
+    if (!ctx || !handle) return RVPT_B200_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == RVPT_B200_IPC_HANDLE_BYTES, "IPC handle size");
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_out_raster)
+    {
+        CU(cudaMalloc(&ctx->d_out_raster, (size_t)ctx->W * ctx->H * 4));
+        CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_out_raster));
+    std::memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int rvpt_b200_attach_output(rvpt_b200_ctx* ctx, const unsigned char handle[64])
+{
+    if (!ctx || !handle) return RVPT_B200_EINVAL;
+    if (ctx->peer_out_raster) return fail(ctx, RVPT_B200_EINVAL, "an output image is already attached");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_out_raster = (uchar4*)ptr;
     return 0;
 }
 

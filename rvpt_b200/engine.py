@@ -180,6 +180,23 @@ class Engine:
     def set_external_tiles(self, d_accum: int | None, d_rgba8: int | None) -> None:
         self._check(self._lib.rvpt_b200_set_external_tiles(self._ctx, d_accum, d_rgba8))
 
-    def untile(self, d_gathered: int, d_raster: int, elem_bytes: int) -> None:
-        self._check(self._lib.rvpt_b200_untile(self._ctx, d_gathered, d_raster, elem_bytes,
-                                               self.nranks))
+    def export_output(self) -> bytes:
+        """Display rank: CUDA IPC handle of the raster result image."""
+        buf = (C.c_ubyte * 64)()
+        self._check(self._lib.rvpt_b200_export_output(self._ctx, buf))
+        return bytes(buf)
+
+    def attach_output(self, handle: bytes) -> None:
+        """Other ranks: write finished pixels straight into the display rank's image."""
+        assert len(handle) == 64
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.rvpt_b200_attach_output(self._ctx, buf))
+
+    def untile(self, d_gathered: int, d_raster: int, elem_bytes: int,
+               cuda_stream: int | None = None) -> None:
+        if cuda_stream is None:
+            self._check(self._lib.rvpt_b200_untile(self._ctx, d_gathered, d_raster, elem_bytes,
+                                                   self.nranks))
+        else:
+            self._check(self._lib.rvpt_b200_untile_on(self._ctx, d_gathered, d_raster, elem_bytes,
+                                                      self.nranks, cuda_stream))
