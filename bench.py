@@ -50,7 +50,7 @@ UNIT = "Msamples/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
@@ -88,56 +88,63 @@ def workload(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clocks and throttle reasons DURING the timed region. Polls NVML (the
+    library behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,
+    clocks_event_reasons.*`) every 2 ms from a thread between start() and stop()."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {  # nvmlClocksEventReason* bits -> the nvidia-smi field names
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+        0x4: "sw_power_cap",
+    }
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, int]] = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "20", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.err = f"NVML unavailable: {exc}"
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except AttributeError:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(mask)))
+            except Exception as exc:  # noqa: BLE001
+                self.err = str(exc)
+                break
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "n/a"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=1)
+        sm = [m for m, _ in self.samples]
+        reasons = set()
+        for _, mask in self.samples:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -357,11 +364,19 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback"
     achieved = frame_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     frame_ms = total_ms / (args.steps * F)
+    # dram__bytes_read.sum + dram__bytes_write.sum per k_frame launch from the committed
+    # `ncu --set full` capture of this command (profiles/), valid for the default workload only
+    traffic = None
+    tpath = ROOT / "profiles" / "k_frame_traffic.json"
+    default_wl = (args.scene, args.pose, W, H, args.bounces, args.aa, world) == \
+        ("builtin", "default", 1920, 1080, 8, 1, 1)
+    if tpath.exists() and default_wl:
+        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
     roofline = {
         "bound": "hbm", "kernel": "k_frame (one persistent cooperative launch per frame: primary "
                                   "wave + bounce waves + in-place accumulation)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic,
         "bytes_per_launch": frame_bytes, "ms_per_launch": kernel_ms,
         "survey_8d_formula_bytes": survey_bytes,
         "survey_8d_formula_gbs": survey_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
