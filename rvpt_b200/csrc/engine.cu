@@ -662,6 +662,21 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     return 0;
 }
 
+extern "C" int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs,
+                                       const float camera[20], uint32_t n_frames)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (!rs) return fail(ctx, RVPT_B200_EINVAL, "null settings");
+    rvpt_render_settings s = *rs;
+    for (uint32_t i = 0; i < n_frames; ++i)
+    {
+        const int rc = rvpt_b200_render_frame(ctx, &s, camera);
+        if (rc) return rc;
+        s.current_frame++;
+    }
+    return 0;
+}
+
 extern "C" int rvpt_b200_sync(rvpt_b200_ctx* ctx)
 {
     if (!ctx) return RVPT_B200_EINVAL;

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/rvpt_abi.h"
 #include "../../include/rvpt_math.h"
 #include "device_scene.h"
@@ -109,39 +111,81 @@ __device__ __forceinline__ void stage_scene(unsigned char* smem_blob, uint64_t* 
 
 /* ---- scene view ---------------------------------------------------------- */
 
-struct SceneView
+/* Where the scene lives for this kernel instance. kSmem: 32-bit shared-space
+ * addresses, read with explicit ld.shared (the generic-pointer form made ptxas
+ * re-derive the shared window base — S2UR/ULEA — inside the node loop);
+ * otherwise generic pointers into the L2-resident blob, read through the
+ * read-only path. All element sizes are powers of two. */
+template <bool kSmem>
+struct SceneViewT
 {
-    const float4* nodes; /* 2 per node */
-    const float4* tris;  /* 4 per triangle */
-    const uint32_t* meta;
-    const float4* mats;  /* 3 per material */
+    typedef typename std::conditional<kSmem, uint32_t, uintptr_t>::type addr_t;
+    addr_t nodes; /* 2 float4 per node */
+    addr_t tris;  /* 4 float4 per triangle */
+    addr_t meta;  /* u32 per triangle */
+    addr_t mats;  /* 3 float4 per material */
     /* primary-wave copies relative to the shared camera origin (kRel only):
      * node bounds minus origin, and dot(v0 - origin, n) per triangle — the
      * first operations of intersect_aabb / intersect_triangle_fast, which are
      * identical for every primary ray of a pinhole or spherical camera. */
-    const float4* rel_nodes;
-    const float* rel_num;
+    addr_t rel_nodes;
+    addr_t rel_num;
 };
 
-__device__ __forceinline__ SceneView make_view(const unsigned char* base, const SceneLayout& L)
+template <bool kSmem, typename A>
+__device__ __forceinline__ float4 ld_f4(A base, uint32_t idx)
 {
-    SceneView v;
-    v.nodes = reinterpret_cast<const float4*>(base);
-    v.tris = reinterpret_cast<const float4*>(base + L.off_tris);
-    v.meta = reinterpret_cast<const uint32_t*>(base + L.off_meta);
-    v.mats = reinterpret_cast<const float4*>(base + L.off_mats);
-    v.rel_nodes = nullptr;
-    v.rel_num = nullptr;
+    if constexpr (kSmem)
+    {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"((uint32_t)base + idx * 16u));
+        return v;
+    }
+    else
+        return __ldg(reinterpret_cast<const float4*>(base) + idx);
+}
+
+template <bool kSmem, typename A>
+__device__ __forceinline__ uint32_t ld_u32(A base, uint32_t idx)
+{
+    if constexpr (kSmem)
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)base + idx * 4u));
+        return v;
+    }
+    else
+        return __ldg(reinterpret_cast<const uint32_t*>(base) + idx);
+}
+
+template <bool kSmem>
+__device__ __forceinline__ SceneViewT<kSmem> make_view(const unsigned char* base, const SceneLayout& L)
+{
+    typedef typename SceneViewT<kSmem>::addr_t addr_t;
+    addr_t b;
+    if constexpr (kSmem)
+        b = smem_u32(base);
+    else
+        b = reinterpret_cast<uintptr_t>(base);
+    SceneViewT<kSmem> v;
+    v.nodes = b;
+    v.tris = b + L.off_tris;
+    v.meta = b + L.off_meta;
+    v.mats = b + L.off_mats;
+    v.rel_nodes = 0;
+    v.rel_num = 0;
     return v;
 }
 
 /* ---- nearest hit: stackless walk in the reference's visiting order ------- */
 
-template <bool kRel>
-__device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f3 d, float& best_t,
-                                              uint32_t& best_tri)
+template <bool kSmem, bool kRel>
+__device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d,
+                                              float& best_t, uint32_t& best_tri)
 {
-    const float4* __restrict__ nodes = kRel ? sc.rel_nodes : sc.nodes;
+    const typename SceneViewT<kSmem>::addr_t nodes = kRel ? sc.rel_nodes : sc.nodes;
     /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
     const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
     best_t = RV_INF;
@@ -149,8 +193,8 @@ __device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
-        const float4 n0 = nodes[2 * node];
-        const float4 n1 = nodes[2 * node + 1];
+        const float4 n0 = ld_f4<kSmem>(nodes, 2 * node);
+        const float4 n1 = ld_f4<kSmem>(nodes, 2 * node + 1);
         float fx, nx, fy, ny, fz, nz;
         if (kRel)
         {
@@ -181,18 +225,18 @@ __device__ __forceinline__ void trace_nearest(const SceneView& sc, rv_f3 o, rv_f
                     /* intersect_triangle_fast (intersection.glsl:267-323) on the
                      * precomputed record; the early-out is value-neutral because
                      * the acceptance test is a pure conjunction. */
-                    const float4 A = sc.tris[4 * i + 0];
-                    const float4 B = sc.tris[4 * i + 1];
-                    m = sc.meta[i];
-                    const float num = kRel ? sc.rel_num[i]
+                    const float4 A = ld_f4<kSmem>(sc.tris, 4 * i + 0);
+                    const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
+                    m = ld_u32<kSmem>(sc.meta, i);
+                    const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, i))
                                            : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
                                                     rv_make(B.x, B.y, B.z));
                     const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
                     const float t = num / den;
                     if (0.0f < t && t < best_t)
                     {
-                        const float4 C = sc.tris[4 * i + 2];
-                        const float4 D = sc.tris[4 * i + 3];
+                        const float4 C = ld_f4<kSmem>(sc.tris, 4 * i + 2);
+                        const float4 D = ld_f4<kSmem>(sc.tris, 4 * i + 3);
                         const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
                         const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
                         const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
@@ -311,12 +355,12 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
-template <bool kRel>
-__device__ __forceinline__ bool kajiya_step(const SceneView& sc, PathState& s, rv_f3& sample)
+template <bool kSmem, bool kRel>
+__device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
-    trace_nearest<kRel>(sc, s.o, s.d, t, tri);
+    trace_nearest<kSmem, kRel>(sc, s.o, s.d, t, tri);
 
     if (tri == 0xFFFFFFFFu)
     {
@@ -327,10 +371,10 @@ __device__ __forceinline__ bool kajiya_step(const SceneView& sc, PathState& s, r
         return false;
     }
 
-    const float4 B = sc.tris[4 * tri + 1];
-    const uint32_t mi = sc.meta[tri] & ~RVPT_TRI_LAST;
-    const float4 M0 = sc.mats[3 * mi + 0];
-    const float4 M1 = sc.mats[3 * mi + 1];
+    const float4 B = ld_f4<kSmem>(sc.tris, 4 * tri + 1);
+    const uint32_t mi = ld_u32<kSmem>(sc.meta, tri) & ~RVPT_TRI_LAST;
+    const float4 M0 = ld_f4<kSmem>(sc.mats, 3 * mi + 0);
+    const float4 M1 = ld_f4<kSmem>(sc.mats, 3 * mi + 1);
     const int type = __float_as_int(M1.w);
 
     /* intersect_scene (intersection.glsl:511-513) */
@@ -358,7 +402,7 @@ __device__ __forceinline__ bool kajiya_step(const SceneView& sc, PathState& s, r
     if (type == 0)
     {
         /* Lambert :617-623, material.glsl:96-108, samples_mapping.glsl:39-60,112-131 */
-        const float4 M2 = sc.mats[3 * mi + 2];
+        const float4 M2 = ld_f4<kSmem>(sc.mats, 3 * mi + 2);
         const float u = rv_rand(&s.rng);
         const float v = rv_rand(&s.rng);
         const float phi = RV_TWO_PI * u;
@@ -503,8 +547,8 @@ __device__ __forceinline__ void clear_next_counters(const FrameParams& p)
 }
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
-template <bool kRel>
-__device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneView& sc)
+template <bool kSmem, bool kRel>
+__device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneViewT<kSmem>& sc)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const uint32_t lane = threadIdx.x & 31u;
@@ -579,7 +623,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
             rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
             if (p.max_bounces > 0)
             {
-                alive = kajiya_step<kRel>(sc, s, sample);
+                alive = kajiya_step<kSmem, kRel>(sc, s, sample);
                 if (alive && p.max_bounces == 1)
                 {
                     alive = false; /* :674-675 ran out of iterations */
@@ -626,7 +670,8 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
  */
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_IN_THREAD 2u
-__device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneView& sc, int b,
+template <bool kSmem>
+__device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
                                              uint32_t count, uint32_t mode)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
@@ -677,7 +722,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             rv_f3 sample;
             for (int k = b;; ++k)
             {
-                alive = kajiya_step<false>(sc, s, sample);
+                alive = kajiya_step<kSmem, false>(sc, s, sample);
                 if (alive && k == p.max_bounces - 1)
                 {
                     alive = false; /* integrators.glsl:674-675: col is discarded */
@@ -703,12 +748,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 
     clear_next_counters(p);
-    SceneView sc;
-    if (kSmem)
+    SceneViewT<kSmem> sc;
+    if constexpr (kSmem)
     {
         stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view(smem, p.layout);
-        if (kRel)
+        sc = make_view<true>(smem, p.layout);
+        if constexpr (kRel)
         {
             /* origin-relative copies for the primary wave (same subtractions /
              * dot product every primary ray would do: cam.matrix[3].xyz is the
@@ -718,24 +763,24 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
             const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
             for (uint32_t i = threadIdx.x; i < p.layout.n_nodes; i += blockDim.x)
             {
-                const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+                const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
                 rel_nodes[2 * i] = make_float4(n0.x - o.x, n0.y - o.x, n0.z - o.y, n0.w - o.y);
                 rel_nodes[2 * i + 1] = make_float4(n1.x - o.z, n1.y - o.z, n1.z, n1.w);
             }
             for (uint32_t i = threadIdx.x; i < p.layout.n_tris; i += blockDim.x)
             {
-                const float4 A = sc.tris[4 * i], B = sc.tris[4 * i + 1];
+                const float4 A = ld_f4<true>(sc.tris, 4 * i), B = ld_f4<true>(sc.tris, 4 * i + 1);
                 rel_num[i] = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
             }
-            sc.rel_nodes = rel_nodes;
-            sc.rel_num = rel_num;
+            sc.rel_nodes = smem_u32(rel_nodes);
+            sc.rel_num = smem_u32(rel_num);
             __syncthreads();
         }
     }
     else
-        sc = make_view(p.scene, p.layout);
+        sc = make_view<false>(p.scene, p.layout);
 
-    primary_phase<kRel>(p, sc);
+    primary_phase<kSmem, kRel>(p, sc);
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     for (int b = 1; b < p.max_bounces; ++b)
@@ -748,10 +793,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_frame(const FrameParams p)
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         if (count <= p.tail_threshold)
         {
-            bounce_phase(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
+            bounce_phase<kSmem>(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
             break;
         }
-        bounce_phase(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+        bounce_phase<kSmem>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
     }
 }
 
@@ -764,15 +809,15 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     clear_next_counters(p);
-    SceneView sc;
-    if (kSmem)
+    SceneViewT<kSmem> sc;
+    if constexpr (kSmem)
     {
         stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view(smem, p.layout);
+        sc = make_view<true>(smem, p.layout);
     }
     else
-        sc = make_view(p.scene, p.layout);
-    primary_phase<false>(p, sc);
+        sc = make_view<false>(p.scene, p.layout);
+    primary_phase<kSmem, false>(p, sc);
 }
 
 template <bool kSmem>
@@ -787,16 +832,16 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
         atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
 
-    SceneView sc;
-    if (kSmem)
+    SceneViewT<kSmem> sc;
+    if constexpr (kSmem)
     {
         stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view(smem, p.layout);
+        sc = make_view<true>(smem, p.layout);
     }
     else
-        sc = make_view(p.scene, p.layout);
+        sc = make_view<false>(p.scene, p.layout);
     const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-    bounce_phase(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+    bounce_phase<kSmem>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
 }
 
 /* ======================================================================== */

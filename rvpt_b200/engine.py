@@ -124,8 +124,16 @@ class Engine:
         assert cam.size == 20
         self._check(self._lib.rvpt_b200_render_frame(self._ctx, rs.ctypes.data, cam.ctypes.data))
 
-    def render_frame_raw(self, settings_ptr: int, camera_ptr: int) -> None:
-        self._check(self._lib.rvpt_b200_render_frame(self._ctx, settings_ptr, camera_ptr))
+    def render_frames(self, settings: np.ndarray, camera: np.ndarray, n_frames: int) -> None:
+        """n_frames progressive frames starting at settings.current_frame, one launch."""
+        rs = np.ascontiguousarray(settings, RENDER_SETTINGS_DTYPE)
+        cam = np.ascontiguousarray(camera, np.float32)
+        assert cam.size == 20
+        self._check(self._lib.rvpt_b200_render_frames(self._ctx, rs.ctypes.data, cam.ctypes.data,
+                                                      int(n_frames)))
+
+    def render_frame_raw(self, settings_ptr: int, camera_ptr: int, n_frames: int = 1) -> None:
+        self._check(self._lib.rvpt_b200_render_frames(self._ctx, settings_ptr, camera_ptr, n_frames))
 
     def sync(self) -> None:
         self._check(self._lib.rvpt_b200_sync(self._ctx))

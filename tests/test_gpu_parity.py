@@ -159,6 +159,29 @@ def test_gpu_matches_committed_golden_pins(rv, oracle_mod, builtin, cornell):
         eng.close()
 
 
+@pytest.mark.parametrize("aa", [1, 2])
+def test_multi_frame_launch_equals_frame_by_frame(rv, oracle_mod, cornell, aa):
+    """rvpt_b200_render_frames(n) == n x render_frame with current_frame++ ==
+    the oracle, including a batch that does not start at frame 0."""
+    W, H = 144, 96
+    cam = rv.camera_data(translation=CORNELL_POSE, aspect=W / H, fov=60.0)
+    one = rv.Engine(W, H)
+    one.upload_scene(cornell.triangles, cornell.materials, cornell.nodes)
+    batch = rv.Engine(W, H)
+    batch.upload_scene(cornell.triangles, cornell.materials, cornell.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, cornell.triangles, cornell.materials, cornell.nodes)
+    for f in range(7):
+        rs = rv.default_settings(frame=f, aa=aa)
+        one.render_frame(rs, cam)
+        ora.render_frame(rs, cam)
+    batch.render_frames(rv.default_settings(frame=0, aa=aa), cam, 3)
+    batch.render_frames(rv.default_settings(frame=3, aa=aa), cam, 4)
+    _assert_bit_equal(batch.read_accum_f32(), ora.accum, "multi-frame launch vs oracle")
+    _assert_bit_equal(batch.read_accum_f32(), one.read_accum_f32(), "multi-frame vs frame by frame")
+    assert np.array_equal(batch.read_output_rgba8(), one.read_output_rgba8())
+    assert batch.stats()["active"] == ora.active_list()  # stats of the last frame
+
+
 def test_unfused_waves_equal_fused_frame_kernel(rv, oracle_mod, cornell):
     """One launch per wave (UNFUSED) and the persistent cooperative k_frame are
     the same computation."""

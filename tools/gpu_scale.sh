@@ -1,0 +1,24 @@
+#!/bin/bash
+# strong-scaling run on one box: N = 1, 2, 4, 8 (subset of the visible GPUs), p2p fused output
+mkdir -p gpurun_out
+TAG=${1:-r01}
+for n in 1 2 4 8; do
+  if [ $n -eq 1 ]; then timeout 200 python bench.py --steps 100 > gpurun_out/scale_${TAG}_n$n.json 2>gpurun_out/scale_${TAG}_n$n.err;
+  else timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 100 > gpurun_out/scale_${TAG}_n$n.json 2>gpurun_out/scale_${TAG}_n$n.err; fi
+  grep -iE "error|Traceback" gpurun_out/scale_${TAG}_n$n.err | head -3
+  python - <<PY
+import json
+l=[x for x in open('gpurun_out/scale_${TAG}_n$n.json') if x.startswith('{')]
+d=json.loads(l[-1]); print('N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'us/frame', round(d['ms_per_step']/d['config']['frames_per_step']*1000,1), '|', d['config']['gather'][:30], '|', d['config']['launch'][:30], d['clocks'])
+PY
+done
+# C4: 3840x2160, 16 spp, 8 GPUs vs 1 GPU
+for n in 1 8; do
+  if [ $n -eq 1 ]; then timeout 200 python bench.py --steps 30 --width 3840 --height 2160 --no-cpu-baseline > gpurun_out/c4_${TAG}_n$n.json 2>gpurun_out/c4_${TAG}_n$n.err;
+  else timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 30 --width 3840 --height 2160 > gpurun_out/c4_${TAG}_n$n.json 2>gpurun_out/c4_${TAG}_n$n.err; fi
+  python - <<PY
+import json
+l=[x for x in open('gpurun_out/c4_${TAG}_n$n.json') if x.startswith('{')]
+d=json.loads(l[-1]); print('C4 4K N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'us/frame', round(d['ms_per_step']/d['config']['frames_per_step']*1000,1))
+PY
+done
