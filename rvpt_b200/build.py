@@ -23,6 +23,8 @@ LIB = HERE / "librvpt_b200.so"
 
 CUDA_SOURCES = ["kernels.cu", "engine.cu"]
 HOST_SOURCES = ["bvh_build.cpp", "camera.cpp"]
+HEADLESS = HERE / "rvpt_headless"
+HEADLESS_SOURCES = [CSRC / "host" / "rvpt_host.cpp", CSRC / "host" / "rvpt_headless.cpp"]
 HEADERS = [CSRC / "device_scene.h", CSRC / "kernels.h", ROOT / "include" / "rvpt_abi.h",
            ROOT / "include" / "rvpt_math.h"]
 
@@ -46,7 +48,10 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in CUDA_SOURCES + HOST_SOURCES] + HEADERS + [Path(__file__)]
+    deps = ([CSRC / s for s in CUDA_SOURCES + HOST_SOURCES] + HEADERS + [Path(__file__)]
+            + HEADLESS_SOURCES + [CSRC / "host" / "rvpt_host.h"])
+    if not HEADLESS.exists():
+        return True
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -70,6 +75,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
            "-o", str(tmp), *objs]
     subprocess.run(cmd, check=True)
     os.replace(tmp, LIB)
+    # the C++ host mirror (RVPT / Camera / load_model) + headless driver, linked against the C ABI
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", str(HEADLESS),
+           *[str(s) for s in HEADLESS_SOURCES], str(LIB), f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
     return LIB
 
 

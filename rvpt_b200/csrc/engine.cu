@@ -51,6 +51,9 @@ struct rvpt_b200_ctx
 
     /* scene */
     unsigned char* d_scene = nullptr;
+    unsigned char* h_scene_pinned = nullptr; /* staging copy of the blob */
+    size_t scene_capacity = 0;
+    cudaEvent_t scene_copied = nullptr;
     SceneLayout layout{};
     bool scene_smem = false;
     bool have_scene = false;
@@ -403,26 +406,49 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     std::memcpy(blob.data() + L.off_mats, ps.mats.data(), ps.mats.size() * sizeof(DevMaterial));
 
     CU(cudaSetDevice(ctx->device));
-    /* frames in flight still read the old blob */
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_scene);
-    ctx->d_scene = nullptr;
-    CU(cudaMalloc(&ctx->d_scene, L.bytes));
-    CU(cudaMemcpyAsync(ctx->d_scene, blob.data(), L.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream)); /* blob is a stack temporary */
-    ctx->layout = L;
-    ctx->scene_smem = rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris) <= RVPT_SMEM_SCENE_LIMIT;
+    /* The reference re-uploads its scene buffers every frame (rvpt.cpp:123-126), so this
+     * path is kept cheap: the device blob and the pinned staging copy are reused while they
+     * are large enough, the copy is ordered on the ctx stream behind the frames that still
+     * read the old blob (no host synchronisation before it), and launch geometry is only
+     * re-derived when the blob's shape changes. */
+    if (L.bytes > ctx->scene_capacity)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_scene);
+        if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
+        ctx->d_scene = nullptr;
+        ctx->h_scene_pinned = nullptr;
+        ctx->scene_capacity = 0;
+        const size_t cap = ((size_t)L.bytes + 4095) & ~(size_t)4095;
+        CU(cudaMalloc(&ctx->d_scene, cap));
+        CU(cudaMallocHost(&ctx->h_scene_pinned, cap));
+        ctx->scene_capacity = cap;
+    }
+    else
+        CU(cudaEventSynchronize(ctx->scene_copied)); /* the previous upload has left the staging copy */
+    std::memcpy(ctx->h_scene_pinned, blob.data(), L.bytes);
+    CU(cudaMemcpyAsync(ctx->d_scene, ctx->h_scene_pinned, L.bytes, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaEventRecord(ctx->scene_copied, ctx->stream));
 
-    int occ_f = 0, occ_p = 0, occ_b = 0;
-    if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
-    CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes, L.n_nodes, L.n_tris));
-    if (occ_f < 1 || occ_p < 1 || occ_b < 1)
-        return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)", occ_f,
-                    occ_p, occ_b);
-    /* persistent grids: every CTA is resident (a requirement of the cooperative launch) */
-    ctx->grid_frame = ctx->num_sms * occ_f;
-    ctx->grid_primary = ctx->num_sms * occ_p;
-    ctx->grid_bounce = ctx->num_sms * occ_b;
+    const bool same_shape = ctx->have_scene && L.bytes == ctx->layout.bytes &&
+                            L.n_nodes == ctx->layout.n_nodes && L.n_tris == ctx->layout.n_tris;
+    ctx->layout = L;
+    if (!same_shape)
+    {
+        ctx->scene_smem =
+            rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris) <= RVPT_SMEM_SCENE_LIMIT;
+        int occ_f = 0, occ_p = 0, occ_b = 0;
+        if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
+        CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes, L.n_nodes, L.n_tris));
+        if (occ_f < 1 || occ_p < 1 || occ_b < 1)
+            return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)",
+                        occ_f, occ_p, occ_b);
+        /* persistent grids: every CTA is resident (a requirement of the cooperative launch) */
+        ctx->grid_frame = ctx->num_sms * occ_f;
+        ctx->grid_primary = ctx->num_sms * occ_p;
+        ctx->grid_bounce = ctx->num_sms * occ_b;
+    }
     ctx->have_scene = true;
     return 0;
 }
@@ -480,6 +506,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
                     device, prop.major, prop.minor);
     ctx->num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->scene_copied, cudaEventDisableTiming));
     ctx->stream = ctx->own_stream;
     return 0;
 }
@@ -494,6 +521,8 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
         if (ctx->peer_out_raster) cudaIpcCloseMemHandle(ctx->peer_out_raster);
         free_frame_buffers(ctx);
         cudaFree(ctx->d_scene);
+        if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
+        if (ctx->scene_copied) cudaEventDestroy(ctx->scene_copied);
         for (auto& t : ctx->timed) ctx->event_pool.push_back(t);
         for (auto& t : ctx->event_pool)
         {

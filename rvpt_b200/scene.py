@@ -64,6 +64,17 @@ def parse_obj(text: str) -> tuple[np.ndarray, np.ndarray]:
             np.asarray(faces, dtype=np.int32).reshape(-1, 3))
 
 
+def write_obj(path, vertices: np.ndarray, faces: np.ndarray) -> None:
+    """Writes positions + triangles as a Wavefront OBJ (9 significant digits, so
+    parsing it back reproduces the float32 values)."""
+    with open(path, "w") as f:
+        f.write("o mesh\n")
+        for v in np.asarray(vertices, np.float32):
+            f.write("v %.9g %.9g %.9g\n" % (v[0], v[1], v[2]))
+        for t in np.asarray(faces):
+            f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+
+
 def make_triangles(v0: np.ndarray, v1: np.ndarray, v2: np.ndarray, material_id) -> np.ndarray:
     """`Triangle(v0, v1, v2, material_id)` (src/rvpt/geometry.h:81-91): the
     face normal normalize(cross(v1-v0, v2-v0)) is packed into the three .w."""

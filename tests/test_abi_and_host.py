@@ -192,3 +192,32 @@ def test_product_does_not_import_the_oracle():
     for path in (ROOT / "rvpt_b200").rglob("*"):
         if path.suffix in {".py", ".cu", ".cpp", ".h"}:
             assert not banned.search(path.read_text()), path
+
+
+HEADLESS = ROOT / "rvpt_b200" / "rvpt_headless"
+
+
+def test_headless_driver_cli(rv, tmp_path):
+    """The C++ host mirror (RVPT / Camera / load_model + main loop of main.cpp)
+    is built next to the library; argument and model errors are reported, and
+    without a GPU initialisation fails loudly instead of rendering on the CPU."""
+    import subprocess
+    import torch
+    assert HEADLESS.exists(), "python -m rvpt_b200.build builds rvpt_headless"
+    assert subprocess.run([str(HEADLESS), "--help"], capture_output=True).returncode == 0
+    r = subprocess.run([str(HEADLESS), str(tmp_path / "missing.obj")], capture_output=True, text=True)
+    assert r.returncode == 1 and "MODEL-LOADING" in r.stderr
+    if not torch.cuda.is_available():
+        from rvpt_b200.scene import builtin_mesh, write_obj
+        obj = tmp_path / "bunny.obj"
+        write_obj(obj, *builtin_mesh())
+        r = subprocess.run([str(HEADLESS), str(obj), "--frames", "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "failed to initialize RVPT" in r.stderr
+
+
+def test_obj_roundtrip_preserves_float32(rv, tmp_path):
+    from rvpt_b200.scene import builtin_mesh, parse_obj, write_obj
+    v, f = builtin_mesh()
+    write_obj(tmp_path / "m.obj", v, f)
+    v2, f2 = parse_obj((tmp_path / "m.obj").read_text())
+    assert np.array_equal(v.view(np.uint32), v2.view(np.uint32)) and np.array_equal(f, f2)

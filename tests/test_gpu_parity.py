@@ -327,3 +327,30 @@ def test_full_size_1080p_properties(rv, oracle_mod, builtin):
     assert st["samples"] == W * H
     assert st["segments"] == sum(st["active"])
     assert g[1079].any(), "rows >= 1072 are rendered unless REFERENCE_DISPATCH is set"
+
+
+def test_cpp_headless_driver_matches_python_host(rv, builtin, tmp_path):
+    """f-2: the C++ mirror of main.cpp's loop (load_model -> add_material ->
+    initialize -> update/draw) produces the same image as the Python host."""
+    import subprocess
+    from pathlib import Path
+    from rvpt_b200.scene import builtin_mesh, write_obj
+    exe = Path(rv.__file__).parent / "rvpt_headless"
+    obj, ppm = tmp_path / "bunny.obj", tmp_path / "out.ppm"
+    write_obj(obj, *builtin_mesh())
+    W, H, frames = 320, 176, 8
+    r = subprocess.run([str(exe), str(obj), "--width", str(W), "--height", str(H), "--frames",
+                        str(frames), "--translate", "0", "0.8", "-2.5", "--out", str(ppm)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = ppm.read_bytes()
+    header = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(header)
+    img = np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3)
+
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    for f in range(frames):  # update(): first frame is 0, then ++ (rvpt.cpp:102-111)
+        eng.render_frame(rv.default_settings(frame=f), cam)
+    assert np.array_equal(img, eng.read_output_rgba8()[..., :3])
