@@ -312,6 +312,75 @@ bool intersect_list(const Scene& sc, const Ray& ray, float mint, float maxt, Ise
     return closest_t < maxt;
 }
 
+/* intersection.glsl:417-463 — early out at the first accepted triangle */
+bool intersect_bvh_any(const Scene& sc, const Ray& ray, float mint, float maxt, bool* stack_overflow)
+{
+    uint32_t stack[64];
+    int stack_ptr = 0;
+    float closest_t = maxt;
+
+    stack[stack_ptr++] = ~0u;
+    uint32_t stack_top = 0;
+    while (stack_top != ~0u)
+    {
+        const rvpt_bvh_node& node = sc.nodes[stack_top];
+        rv_f3 node_min = rv_make(node.bounds[0], node.bounds[2], node.bounds[4]);
+        rv_f3 node_max = rv_make(node.bounds[1], node.bounds[3], node.bounds[5]);
+        if (!intersect_aabb(ray, node_min, node_max, mint, closest_t))
+        {
+            stack_top = stack[--stack_ptr];
+            continue;
+        }
+        uint32_t first_child_or_primitive = node.first_child_or_primitive;
+        if (node.primitive_count > 0)
+        {
+            for (uint32_t i = first_child_or_primitive, n = i + node.primitive_count; i < n; ++i)
+            {
+                const rvpt_triangle& tri = sc.tris[i];
+                Isect temp;
+                if (intersect_triangle_fast(ray, rv_make(tri.vertex0[0], tri.vertex0[1], tri.vertex0[2]),
+                                            rv_make(tri.vertex1[0], tri.vertex1[1], tri.vertex1[2]),
+                                            rv_make(tri.vertex2[0], tri.vertex2[1], tri.vertex2[2]),
+                                            mint, closest_t, temp))
+                    return true;
+            }
+            stack_top = stack[--stack_ptr];
+        }
+        else
+        {
+            if (stack_ptr >= 64)
+            {
+                *stack_overflow = true;
+                return false;
+            }
+            stack[stack_ptr++] = first_child_or_primitive + 1;
+            stack_top = first_child_or_primitive;
+        }
+    }
+    return false;
+}
+
+/* intersection.glsl:467-485 */
+bool intersect_scene_any(const Scene& sc, const Ray& ray, float mint, float maxt,
+                         bool* stack_overflow)
+{
+    if (sc.brute_force)
+    {
+        for (size_t i = 0; i < sc.n_tris; ++i)
+        {
+            const rvpt_triangle& tri = sc.tris[i];
+            Isect temp;
+            if (intersect_triangle_fast(ray, rv_make(tri.vertex0[0], tri.vertex0[1], tri.vertex0[2]),
+                                        rv_make(tri.vertex1[0], tri.vertex1[1], tri.vertex1[2]),
+                                        rv_make(tri.vertex2[0], tri.vertex2[1], tri.vertex2[2]), mint,
+                                        maxt, temp))
+                return true;
+        }
+        return false;
+    }
+    return intersect_bvh_any(sc, ray, mint, maxt, stack_overflow);
+}
+
 /* intersection.glsl:489-517 */
 bool intersect_scene(const Scene& sc, const Ray& ray, float mint, float maxt, Isect& info,
                      bool* stack_overflow)
@@ -477,8 +546,260 @@ rv_f3 integrator_Kajiya(const Scene& sc, Ray primary_ray, float mint, float maxt
     return rv_make(0, 0, 0);
 }
 
+rv_f3 splat(float v) { return rv_make(v, v, v); }
+
+/* the directional light of the Utah / Appel / Whitted models: normalize(vec3(0.5,1,0.3)) */
+rv_f3 light_direction() { return rv_normalize(rv_make(0.5f, 1.0f, 0.3f)); }
+
+/* integrators.glsl:24-38 */
+rv_f3 integrator_binary(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    return splat(intersect_scene_any(sc, ray, mint, maxt, &ctr->stack_overflow) ? 1.0f : 0.0f);
+}
+
+/* integrators.glsl:42-59 */
+rv_f3 integrator_color(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    Isect info;
+    if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow)) return splat(0.0f);
+    return info.mat.base_color;
+}
+
+/* integrators.glsl:63-82 */
+rv_f3 integrator_depth(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    Isect info;
+    intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow);
+    float len = sqrtf(rv_dot(ray.direction, ray.direction));
+    float inv_dist = 1.0f / (len * info.t);
+    return splat(inv_dist);
+}
+
+/* integrators.glsl:86-102 */
+rv_f3 integrator_normal(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    Isect info;
+    float isect = intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow) ? 1.0f : 0.0f;
+    float h = 0.5f * isect;
+    return rv_make(0.5f * info.normal.x + h, 0.5f * info.normal.y + h, 0.5f * info.normal.z + h);
+}
+
+/* integrators.glsl:106-148 */
+rv_f3 integrator_Utah(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    rv_f3 light_intensity = splat(1.0f);
+    rv_f3 light_dir = light_direction();
+    rv_f3 ambient = splat(0.1f);
+    Isect info;
+    rv_f3 col = ambient;
+    if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow))
+    {
+        float t = ray.direction.y;
+        return rv_make(rv_mix(1.0f, 0.2f, t), rv_mix(1.0f, 0.3f, t), rv_mix(1.0f, 0.7f, t));
+    }
+    col = rv_add(col, info.mat.emissive);
+    rv_f3 normal = info.normal;
+    normal = rv_dot(ray.direction, normal) < 0.0f ? normal : rv_neg(normal);
+    float cos_light = fmaxf(0.0f, rv_dot(light_dir, normal));
+    return rv_add(col, rv_scale(cos_light, rv_mul(info.mat.base_color, light_intensity)));
+}
+
+/* integrators.glsl:152-200 */
+rv_f3 integrator_ao(const Scene& sc, const Ray& ray, float mint, float maxt, int nrays,
+                    uint32_t* rng, Counters* ctr)
+{
+    Isect info;
+    bool isect = intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow);
+    if (!isect) return splat(0.0f);
+    rv_f3 normal = info.normal;
+    normal = rv_dot(ray.direction, normal) < 0.0f ? normal : rv_neg(normal);
+    float acc = 0.0f;
+    for (int i = 0; i < nrays; ++i)
+    {
+        Ray new_ray;
+        new_ray.origin = rv_add(info.pos, rv_scale(RV_EPSILON, normal));
+        float u = rv_rand(rng);
+        float v = rv_rand(rng);
+        new_ray.direction = map_cosine_hemisphere_simple(u, v, normal);
+        acc += intersect_scene_any(sc, new_ray, mint, maxt, &ctr->stack_overflow) ? 1.0f : 0.0f;
+    }
+    return splat(1.0f - acc / (float)nrays);
+}
+
+/* integrators.glsl:204-250 */
+rv_f3 integrator_Appel(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)
+{
+    rv_f3 light_dir = light_direction();
+    Isect info;
+    if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow)) return splat(1.0f);
+    rv_f3 dir_in = rv_normalize(ray.direction);
+    float cos_view = rv_dot(dir_in, info.normal);
+    rv_f3 normal = cos_view > 0.0f ? rv_neg(info.normal) : info.normal;
+    Ray shadow_ray;
+    shadow_ray.origin = rv_add(info.pos, rv_scale(RV_EPSILON, normal));
+    shadow_ray.direction = light_dir;
+    if (intersect_scene_any(sc, shadow_ray, 0.0f, INF, &ctr->stack_overflow)) return splat(0.0f);
+    float cos_light = fmaxf(0.0f, rv_dot(light_dir, normal));
+    return splat(1.0f * cos_light);
+}
+
+/* Shared by Whitted and Cook: integrators.glsl:290-316 / :439-465 (normal flip, eta)
+ * and the mirror / dielectric branches :338-377 / :487-527, identical to Kajiya's. */
+struct Surface
+{
+    rv_f3 pos, normal, dir_in;
+    float cos_in, eta;
+};
+
+Surface surface_of(const Ray& ray, const Isect& info)
+{
+    Surface s;
+    s.pos = info.pos;
+    s.normal = info.normal;
+    s.dir_in = rv_normalize(ray.direction);
+    float cos_view = rv_dot(s.dir_in, s.normal);
+    s.eta = info.mat.ior;
+    if (cos_view > 0.0f)
+    {
+        s.cos_in = cos_view;
+        s.normal = rv_neg(s.normal);
+    }
+    else
+    {
+        s.cos_in = -cos_view;
+        s.eta = 1.0f / s.eta;
+    }
+    return s;
+}
+
+/* returns false for an unknown material type */
+bool specular_bounce(const Surface& s, const MaterialNew& mat, uint32_t* rng, Ray* ray,
+                     rv_f3* throughput)
+{
+    rv_f3 pos_out, dir_out;
+    if (mat.type == 1)
+    {
+        pos_out = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+        dir_out = rv_add(s.dir_in, rv_scale(s.cos_in + s.cos_in, s.normal));
+    }
+    else if (mat.type == 2)
+    {
+        float cos_out_sqr = 1.0f - (s.eta * s.eta) * (1.0f - s.cos_in * s.cos_in);
+        float cos_out = 0.0f;
+        bool refl = (cos_out_sqr <= 0.0f);
+        if (!refl)
+        {
+            cos_out = sqrtf(fmaxf(0.0f, cos_out_sqr));
+            float f_refl = frensel_reflectance(s.cos_in, cos_out, s.eta);
+            refl = (rv_rand(rng) < f_refl);
+        }
+        if (refl)
+        {
+            pos_out = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+            dir_out = rv_add(s.dir_in, rv_scale(s.cos_in + s.cos_in, s.normal));
+        }
+        else
+        {
+            pos_out = rv_sub(s.pos, rv_scale(RV_EPSILON, s.normal));
+            dir_out = rv_add(rv_scale(s.eta, s.dir_in),
+                             rv_scale(s.eta * s.cos_in - cos_out, s.normal));
+        }
+    }
+    else
+        return false;
+    *throughput = rv_mul(*throughput, mat.base_color);
+    ray->origin = pos_out;
+    ray->direction = dir_out;
+    return true;
+}
+
+rv_f3 sky_no_remap(const Ray& ray) /* mix(white, blue, ray.direction.y), :284 / :433 */
+{
+    float t = ray.direction.y;
+    return rv_make(rv_mix(1.0f, 0.2f, t), rv_mix(1.0f, 0.3f, t), rv_mix(1.0f, 0.7f, t));
+}
+
+/* integrators.glsl:254-403 */
+rv_f3 integrator_Whitted(const Scene& sc, Ray ray, float mint, float maxt, int nbounce,
+                         uint32_t* rng, Counters* ctr)
+{
+    rv_f3 light_intensity = splat(1.0f);
+    rv_f3 light_dir = light_direction();
+    rv_f3 col = splat(0.1f); /* ambient */
+    rv_f3 throughput = splat(1.0f);
+    Isect info;
+    for (int i = 0; i < nbounce; ++i)
+    {
+        if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow))
+            return rv_add(col, rv_mul(throughput, sky_no_remap(ray)));
+        col = rv_add(col, rv_mul(throughput, info.mat.emissive));
+        Surface s = surface_of(ray, info);
+        if (info.mat.type == 0)
+        {
+            Ray shadow_ray;
+            shadow_ray.origin = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+            shadow_ray.direction = light_dir;
+            if (intersect_scene_any(sc, shadow_ray, 0.0f, INF, &ctr->stack_overflow)) return col;
+            float cos_light = fmaxf(0.0f, rv_dot(light_dir, s.normal));
+            rv_f3 lit = rv_scale(cos_light, rv_mul(rv_mul(throughput, info.mat.base_color), light_intensity));
+            return rv_add(col, lit);
+        }
+        if (!specular_bounce(s, info.mat, rng, &ray, &throughput)) return splat(0.0f);
+    }
+    return splat(0.0f);
+}
+
+/* integrators.glsl:407-543 */
+rv_f3 integrator_Cook(const Scene& sc, Ray ray, float mint, float maxt, int nbounce, uint32_t* rng,
+                      Counters* ctr)
+{
+    rv_f3 col = splat(0.0f);
+    rv_f3 throughput = splat(1.0f);
+    Isect info;
+    for (int i = 0; i < nbounce; ++i)
+    {
+        if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow))
+            return rv_add(col, rv_mul(throughput, sky_no_remap(ray)));
+        col = rv_add(col, rv_mul(throughput, info.mat.emissive));
+        Surface s = surface_of(ray, info);
+        if (info.mat.type == 0)
+        {
+            ray.origin = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+            ray.direction = mat_scatter_Lambert_cos(s.normal, rng);
+            throughput = rv_mul(throughput,
+                                mat_eval_Lambert_cos(rv_scale(RV_INV_PI, info.mat.base_color)));
+            if (!intersect_scene(sc, ray, mint, maxt, info, &ctr->stack_overflow))
+                return rv_add(col, rv_mul(throughput, sky_no_remap(ray)));
+            return rv_add(col, rv_mul(throughput, info.mat.emissive));
+        }
+        if (!specular_bounce(s, info.mat, rng, &ray, &throughput)) return splat(0.0f);
+    }
+    return splat(0.0f);
+}
+
+/* compute_pass.comp:68-99. Mode 10+ (integrator_Hart, the sphere-tracing heat map of
+ * distance_functions.glsl) is outside the hot-path scope: *ok = false. */
+rv_f3 eval_integrator(const Scene& sc, int idx, const Ray& ray, int max_bounces, uint32_t* rng,
+                      Counters* ctr, bool* ok)
+{
+    switch (idx)
+    {
+        case 0: return integrator_binary(sc, ray, 0.0f, INF, ctr);
+        case 1: return integrator_color(sc, ray, 0.0f, INF, ctr);
+        case 2: return integrator_depth(sc, ray, 0.0f, INF, ctr);
+        case 3: return integrator_normal(sc, ray, 0.0f, INF, ctr);
+        case 4: return integrator_Utah(sc, ray, 0.0f, INF, ctr);
+        case 5: return integrator_ao(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
+        case 6: return integrator_Appel(sc, ray, 0.0f, INF, ctr);
+        case 7: return integrator_Whitted(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
+        case 8: return integrator_Cook(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
+        case 9: return integrator_Kajiya(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
+        default: *ok = false; return splat(0.0f);
+    }
+}
+
 /* compute_pass.comp:121-167 for one pixel. Returns false for an integrator
- * this oracle does not restate (only mode 9, Kajiya, is on the hot path). */
+ * this oracle does not restate (mode 10+, Hart's sphere tracer). */
 bool shade_pixel(const Scene& sc, const Frame& fr, uint32_t x, uint32_t y, rv_f3 prev_in,
                  rv_f3* out, Counters* ctr)
 {
@@ -501,7 +822,6 @@ bool shade_pixel(const Scene& sc, const Frame& fr, uint32_t x, uint32_t y, rv_f3
     }
     else if (split_x > rs.split_ratio[0])
         integrator_idx = rs.top_right_render_mode;
-    if (integrator_idx != 9) return false;
 
     /* :146-148 */
     float keep = (float)(rs.current_frame < 1u ? rs.current_frame : 1u);
@@ -517,8 +837,10 @@ bool shade_pixel(const Scene& sc, const Frame& fr, uint32_t x, uint32_t y, rv_f3
         cy = 1.0f - cy;
 
         Ray ray = get_camera_ray(fr.cam, rs.camera_mode, cx, cy);
-        sampled = rv_add(sampled,
-                         integrator_Kajiya(sc, ray, 0.0f, INF, rs.max_bounces, &rng_state, ctr));
+        bool ok = true;
+        sampled = rv_add(sampled, eval_integrator(sc, integrator_idx, ray, rs.max_bounces,
+                                                  &rng_state, ctr, &ok));
+        if (!ok) return false;
     }
 
     float aa_f = (float)rs.aa;

@@ -137,6 +137,7 @@ struct FrameParams
     int32_t pass;                 /* sample index inside the frame, 0..aa-1 */
     int32_t camera_mode;
     int32_t modes[4];             /* tl, tr, bl, br */
+    int32_t all_kajiya;           /* all four quadrants use integrator 9 */
     float split_x, split_y;
     /* camera (camera.glsl) */
     float cam[16];                /* column-major */

@@ -600,10 +600,16 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
         return fail(ctx, RVPT_B200_EINVAL, "max_bounces = %d outside [0,64]", rs->max_bounces);
     const int modes[4] = {rs->top_left_render_mode, rs->top_right_render_mode,
                           rs->bottom_left_render_mode, rs->bottom_right_render_mode};
+    bool all_kajiya = true;
     for (int m : modes)
-        if (m != 9)
+    {
+        /* eval_integrator's default case is integrator_Hart, the sphere-tracing heat map of
+         * distance_functions.glsl (compute_pass.comp:96-97) — outside the hot-path scope */
+        if (m < 0 || m > 9)
             return fail(ctx, RVPT_B200_EUNSUPPORTED,
-                        "render mode %d: only integrator 9 (Kajiya) is on the B200 hot path", m);
+                        "render mode %d (integrator_Hart sphere tracer) is not built; modes 0-9 are", m);
+        all_kajiya = all_kajiya && m == 9;
+    }
     int rc = ensure_frame_buffers(ctx);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -635,6 +641,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.aa_f = (float)rs->aa;
     p.camera_mode = rs->camera_mode;
     for (int i = 0; i < 4; ++i) p.modes[i] = modes[i];
+    p.all_kajiya = all_kajiya ? 1 : 0;
     p.split_x = rs->split_ratio[0], p.split_y = rs->split_ratio[1];
     std::memcpy(p.cam, camera, 16 * sizeof(float));
     p.aspect = camera[16], p.hfov = camera[17], p.scale = camera[18];
@@ -681,6 +688,14 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
             }
         }
         ctx->launch_seq++;
+    }
+    if (!all_kajiya && p.n_chunks > 0)
+    {
+        /* pixels of the other integrators (split view / debug views): one in-thread pass */
+        p.pass = 0;
+        ScopedTimer tm(ctx, 1);
+        CU(rvpt::launch_modes(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
+        ++launches;
     }
     ctx->last_stats_set = p.stats_set;
     ctx->frame_seq++;

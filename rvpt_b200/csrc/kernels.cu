@@ -277,6 +277,57 @@ __device__ __forceinline__ void slot_to_xy(const FrameParams& p, uint32_t slot, 
     y = ty * RVPT_TILE_DIM + ((w >> 1) << 2) + (lane >> 3);
 }
 
+/* compute_pass.comp:146-148, 162-166: running mean with the previous image and
+ * the two rgba8 stores, for the frame's mean sample `sampled`. */
+__device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t slot, rv_f3 sampled)
+{
+    rv_f3 prev;
+    const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
+    if (u8)
+    {
+        const uchar4 k = p.accum_u8[slot];
+        prev = rv_make(rv_unorm8_load(k.x), rv_unorm8_load(k.y), rv_unorm8_load(k.z));
+    }
+    else
+    {
+        const float4 a = p.accum_f32[slot];
+        prev = rv_make(a.x, a.y, a.z);
+    }
+    const rv_f3 temporal = rv_make(prev.x * p.keep, prev.y * p.keep, prev.z * p.keep);
+    const rv_f3 acc = rv_make((temporal.x * p.frame_f + sampled.x) * p.inv_frame1,
+                              (temporal.y * p.frame_f + sampled.y) * p.inv_frame1,
+                              (temporal.z * p.frame_f + sampled.z) * p.inv_frame1);
+    const uchar4 q = make_uchar4((unsigned char)rv_unorm8_store(acc.x),
+                                 (unsigned char)rv_unorm8_store(acc.y),
+                                 (unsigned char)rv_unorm8_store(acc.z), 0);
+    if (u8)
+        p.accum_u8[slot] = q;
+    else
+        p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+    if (p.out_raster)
+    {
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        p.out_raster[(size_t)y * p.W + x] = q;
+    }
+    else
+        p.out_tiles[slot] = q;
+}
+
+
+/* compute_pass.comp:134-144: which integrator a pixel uses (4-way split view) */
+__device__ __forceinline__ int integrator_of(const FrameParams& p, uint32_t x, uint32_t y)
+{
+    int idx = p.modes[0];
+    const float sx = (float)x * p.inv_dim_x;
+    const float sy = (float)y * p.inv_dim_y;
+    if (sy > p.split_y)
+        idx = sx < p.split_x ? p.modes[2] : p.modes[3];
+    else if (sx > p.split_x)
+        idx = p.modes[1];
+    return idx;
+}
+
 /* ---- sample termination: compute_pass.comp:146-148, 157-166 --------------- */
 
 /* The previous running mean of a pixel is prefetched towards L1 when its path
@@ -311,38 +362,7 @@ __device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slo
     /* sampled /= aa ; x / 1.0f == x exactly, so the common aa = 1 case skips three divisions */
     const rv_f3 sampled =
         p.aa == 1 ? sum : rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f);
-
-    rv_f3 prev;
-    const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
-    if (u8)
-    {
-        const uchar4 k = p.accum_u8[slot];
-        prev = rv_make(rv_unorm8_load(k.x), rv_unorm8_load(k.y), rv_unorm8_load(k.z));
-    }
-    else
-    {
-        const float4 a = p.accum_f32[slot];
-        prev = rv_make(a.x, a.y, a.z);
-    }
-    const rv_f3 temporal = rv_make(prev.x * p.keep, prev.y * p.keep, prev.z * p.keep);
-    const rv_f3 acc = rv_make((temporal.x * p.frame_f + sampled.x) * p.inv_frame1,
-                              (temporal.y * p.frame_f + sampled.y) * p.inv_frame1,
-                              (temporal.z * p.frame_f + sampled.z) * p.inv_frame1);
-    const uchar4 q = make_uchar4((unsigned char)rv_unorm8_store(acc.x),
-                                 (unsigned char)rv_unorm8_store(acc.y),
-                                 (unsigned char)rv_unorm8_store(acc.z), 0);
-    if (u8)
-        p.accum_u8[slot] = q;
-    else
-        p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
-    if (p.out_raster)
-    {
-        uint32_t x, y;
-        slot_to_xy(p, slot, x, y);
-        p.out_raster[(size_t)y * p.W + x] = q;
-    }
-    else
-        p.out_tiles[slot] = q;
+    accumulate_pixel(p, slot, sampled);
 }
 
 /* ---- one iteration of integrator_Kajiya's loop (integrators.glsl:574-671) -- */
@@ -597,8 +617,10 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
         const uint32_t slot = c * 32u + lane;
         uint32_t x, y;
         slot_to_xy(p, slot, x, y);
+        /* pixels of other integrators (split view) are rendered by k_modes */
         const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
-                            ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
+                            ((slot >> 8) * p.nranks + p.rank < p.n_tiles) &&
+                            (p.all_kajiya || integrator_of(p, x, y) == 9);
         bool alive = false;
         PathState s;
         if (inside)
@@ -845,6 +867,322 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
 }
 
 /* ======================================================================== */
+/* k_modes: the reference's other integrators (compute_pass.comp:68-99)      */
+/* ======================================================================== */
+/* Modes 0-8 — binary, color, depth, normal, Utah, ambient occlusion, Appel,
+ * Whitted, Cook (integrators.glsl:24-543) — are the reference's teaching /
+ * debug views, not the bounce loop: each pixel runs its integrator to the end
+ * inside one thread (all `aa` samples, continuing the pixel's RNG stream), then
+ * accumulates like any other pixel. Launched only when a quadrant asks for one
+ * of them; Kajiya pixels stay on the wavefront path. */
+
+/* intersect_bvh_any (intersection.glsl:417-463): same walk, returns at the
+ * first accepted triangle; closest_t never shrinks. */
+template <bool kSmem>
+__device__ __forceinline__ bool trace_any(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d)
+{
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    uint32_t node = 0;
+    while (node != RVPT_NODE_END)
+    {
+        const float4 n0 = ld_f4<kSmem>(sc.nodes, 2 * node);
+        const float4 n1 = ld_f4<kSmem>(sc.nodes, 2 * node + 1);
+        const float fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
+        const float fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
+        const float fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
+        float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+        float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+        t0 = fmaxf(t0, 0.0f);
+        t1 = fminf(t1, RV_INF);
+        const uint32_t skip = __float_as_uint(n1.z);
+        const uint32_t leaf = __float_as_uint(n1.w);
+        if (t1 >= t0)
+        {
+            if (leaf != RVPT_NODE_INNER)
+            {
+                uint32_t i = leaf, m;
+                do
+                {
+                    const float4 A = ld_f4<kSmem>(sc.tris, 4 * i + 0);
+                    const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
+                    const float4 C = ld_f4<kSmem>(sc.tris, 4 * i + 2);
+                    const float4 D = ld_f4<kSmem>(sc.tris, 4 * i + 3);
+                    m = ld_u32<kSmem>(sc.meta, i);
+                    const float num = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
+                                             rv_make(B.x, B.y, B.z));
+                    const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
+                    const float t = num / den;
+                    const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
+                    const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
+                    const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
+                    const float by = rv_dot(p0, rv_make(D.x, D.y, D.z));
+                    const float m0 = B.w * bx, m1 = C.w * by;
+                    const float m2 = C.w * bx, m3 = D.w * by;
+                    const float u = A.w * (m0 + m1);
+                    const float v = A.w * (m2 + m3);
+                    if (0.0f < t && t < RV_INF && 0.0f < u && 0.0f < v && u + v < 1.0f) return true;
+                    ++i;
+                } while (!(m & RVPT_TRI_LAST));
+                node = skip;
+            }
+            else
+                node = node + 1;
+        }
+        else
+            node = skip;
+    }
+    return false;
+}
+
+struct HitInfo /* Isect + Material_new, intersection.glsl:37-72 */
+{
+    bool hit;
+    float t;
+    rv_f3 pos, normal; /* normal normalised, zero on a miss (intersect_scene :511-513) */
+    rv_f3 base_color, emissive;
+    float ior;
+    int type;
+};
+
+template <bool kSmem>
+__device__ __forceinline__ HitInfo intersect_scene_dev(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d)
+{
+    HitInfo h;
+    uint32_t tri;
+    trace_nearest<kSmem, false>(sc, o, d, h.t, tri);
+    h.hit = tri != 0xFFFFFFFFu;
+    h.pos = rv_make(0.0f, 0.0f, 0.0f);
+    h.normal = rv_make(0.0f, 0.0f, 0.0f);
+    h.base_color = h.emissive = rv_make(0.0f, 0.0f, 0.0f);
+    h.ior = 0.0f;
+    h.type = -1;
+    if (h.hit)
+    {
+        const float4 B = ld_f4<kSmem>(sc.tris, 4 * tri + 1);
+        const uint32_t mi = ld_u32<kSmem>(sc.meta, tri) & ~RVPT_TRI_LAST;
+        const float4 M0 = ld_f4<kSmem>(sc.mats, 3 * mi + 0);
+        const float4 M1 = ld_f4<kSmem>(sc.mats, 3 * mi + 1);
+        h.normal = rv_normalize(rv_make(B.x, B.y, B.z));
+        h.pos = rv_add(o, rv_scale(h.t, d));
+        h.base_color = rv_make(M0.x, M0.y, M0.z);
+        h.ior = M0.w;
+        h.emissive = rv_make(M1.x, M1.y, M1.z);
+        h.type = __float_as_int(M1.w);
+    }
+    return h;
+}
+
+__device__ __forceinline__ rv_f3 splat3(float v) { return rv_make(v, v, v); }
+
+__device__ __forceinline__ rv_f3 sky_no_remap(rv_f3 d) /* mix(white, blue, ray.direction.y) */
+{
+    return rv_make(rv_mix(1.0f, 0.2f, d.y), rv_mix(1.0f, 0.3f, d.y), rv_mix(1.0f, 0.7f, d.y));
+}
+
+/* cosine-weighted scatter around n: material.glsl:96-108, samples_mapping.glsl:39-60,112-131 */
+__device__ __forceinline__ rv_f3 scatter_lambert(rv_f3 n, uint32_t* rng)
+{
+    const float u = rv_rand(rng);
+    const float v = rv_rand(rng);
+    const float phi = RV_TWO_PI * u;
+    const float cos_theta = (1.0f - v) - v;
+    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    float sn, cs;
+    rv_sincos(phi, &sn, &cs);
+    return rv_add(n, rv_make(sin_theta * cs, sin_theta * sn, cos_theta));
+}
+
+struct SurfaceDev
+{
+    rv_f3 pos, normal, dir_in;
+    float cos_in, eta;
+};
+
+/* normal flip / eta selection shared by Whitted, Cook (and Kajiya): integrators.glsl:290-316 */
+__device__ __forceinline__ SurfaceDev surface_of(rv_f3 d, const HitInfo& h)
+{
+    SurfaceDev s;
+    s.pos = h.pos;
+    s.normal = h.normal;
+    s.dir_in = rv_normalize(d);
+    const float cos_view = rv_dot(s.dir_in, s.normal);
+    s.eta = h.ior;
+    if (cos_view > 0.0f)
+    {
+        s.cos_in = cos_view;
+        s.normal = rv_neg(s.normal);
+    }
+    else
+    {
+        s.cos_in = -cos_view;
+        s.eta = 1.0f / s.eta;
+    }
+    return s;
+}
+
+/* mirror / dielectric branches, integrators.glsl:338-377; false = unknown material */
+__device__ __forceinline__ bool specular_bounce(const SurfaceDev& s, const HitInfo& h, uint32_t* rng,
+                                                rv_f3* o, rv_f3* d, rv_f3* thr)
+{
+    if (h.type == 1)
+    {
+        *o = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+        *d = rv_add(s.dir_in, rv_scale(s.cos_in + s.cos_in, s.normal));
+    }
+    else if (h.type == 2)
+    {
+        const float cos_out_sqr = 1.0f - (s.eta * s.eta) * (1.0f - s.cos_in * s.cos_in);
+        float cos_out = 0.0f;
+        bool refl = (cos_out_sqr <= 0.0f);
+        if (!refl)
+        {
+            cos_out = sqrtf(fmaxf(0.0f, cos_out_sqr));
+            const float ec = s.eta * s.cos_in, eo = s.eta * cos_out;
+            const float r_perp = (ec - cos_out) / (ec + cos_out);
+            const float r_par = (s.cos_in - eo) / (s.cos_in + eo);
+            const float f_refl = 0.5f * (r_perp * r_perp + r_par * r_par);
+            refl = (rv_rand(rng) < f_refl);
+        }
+        if (refl)
+        {
+            *o = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+            *d = rv_add(s.dir_in, rv_scale(s.cos_in + s.cos_in, s.normal));
+        }
+        else
+        {
+            *o = rv_sub(s.pos, rv_scale(RV_EPSILON, s.normal));
+            *d = rv_add(rv_scale(s.eta, s.dir_in), rv_scale(s.eta * s.cos_in - cos_out, s.normal));
+        }
+    }
+    else
+        return false;
+    *thr = rv_mul(*thr, h.base_color);
+    return true;
+}
+
+template <bool kSmem>
+__device__ rv_f3 eval_mode(const SceneViewT<kSmem>& sc, int mode, rv_f3 o, rv_f3 d, int max_bounces,
+                           uint32_t* rng)
+{
+    const rv_f3 light_dir = rv_normalize(rv_make(0.5f, 1.0f, 0.3f));
+    if (mode == 0) /* binary :24-38 */
+        return splat3(trace_any<kSmem>(sc, o, d) ? 1.0f : 0.0f);
+    if (mode == 7 || mode == 8)
+    {
+        /* Whitted :254-403, Cook :407-543 */
+        rv_f3 col = mode == 7 ? splat3(0.1f) : splat3(0.0f);
+        rv_f3 thr = splat3(1.0f);
+        for (int i = 0; i < max_bounces; ++i)
+        {
+            HitInfo h = intersect_scene_dev<kSmem>(sc, o, d);
+            if (!h.hit) return rv_add(col, rv_mul(thr, sky_no_remap(d)));
+            col = rv_add(col, rv_mul(thr, h.emissive));
+            const SurfaceDev s = surface_of(d, h);
+            if (h.type == 0)
+            {
+                const rv_f3 o2 = rv_add(s.pos, rv_scale(RV_EPSILON, s.normal));
+                if (mode == 7)
+                {
+                    if (trace_any<kSmem>(sc, o2, light_dir)) return col;
+                    const float cos_light = fmaxf(0.0f, rv_dot(light_dir, s.normal));
+                    const rv_f3 lit = rv_mul(rv_mul(thr, h.base_color), splat3(1.0f));
+                    return rv_add(col, rv_scale(cos_light, lit));
+                }
+                const rv_f3 d2 = scatter_lambert(s.normal, rng);
+                const rv_f3 lam = rv_scale(RV_PI, rv_scale(RV_INV_PI, h.base_color));
+                thr = rv_mul(thr, lam);
+                h = intersect_scene_dev<kSmem>(sc, o2, d2);
+                if (!h.hit) return rv_add(col, rv_mul(thr, sky_no_remap(d2)));
+                return rv_add(col, rv_mul(thr, h.emissive));
+            }
+            if (!specular_bounce(s, h, rng, &o, &d, &thr)) return splat3(0.0f);
+        }
+        return splat3(0.0f);
+    }
+
+    const HitInfo h = intersect_scene_dev<kSmem>(sc, o, d);
+    if (mode == 1) return h.hit ? h.base_color : splat3(0.0f); /* color :42-59 */
+    if (mode == 2)                                              /* depth :63-82 */
+    {
+        const float len = sqrtf(rv_dot(d, d));
+        return splat3(1.0f / (len * h.t));
+    }
+    if (mode == 3) /* normal :86-102 */
+    {
+        const float k = 0.5f * (h.hit ? 1.0f : 0.0f);
+        return rv_make(0.5f * h.normal.x + k, 0.5f * h.normal.y + k, 0.5f * h.normal.z + k);
+    }
+    if (mode == 4) /* Utah :106-148 */
+    {
+        if (!h.hit) return sky_no_remap(d);
+        const rv_f3 col = rv_add(splat3(0.1f), h.emissive);
+        const rv_f3 n = rv_dot(d, h.normal) < 0.0f ? h.normal : rv_neg(h.normal);
+        const float cos_light = fmaxf(0.0f, rv_dot(light_dir, n));
+        return rv_add(col, rv_scale(cos_light, rv_mul(h.base_color, splat3(1.0f))));
+    }
+    if (mode == 5) /* ambient occlusion :152-200, nrays = max_bounces */
+    {
+        if (!h.hit) return splat3(0.0f);
+        const rv_f3 n = rv_dot(d, h.normal) < 0.0f ? h.normal : rv_neg(h.normal);
+        float acc = 0.0f;
+        for (int i = 0; i < max_bounces; ++i)
+        {
+            const rv_f3 o2 = rv_add(h.pos, rv_scale(RV_EPSILON, n));
+            const rv_f3 d2 = scatter_lambert(n, rng);
+            acc += trace_any<kSmem>(sc, o2, d2) ? 1.0f : 0.0f;
+        }
+        return splat3(1.0f - acc / (float)max_bounces);
+    }
+    /* mode 6: Appel :204-250 */
+    if (!h.hit) return splat3(1.0f);
+    const rv_f3 dir_in = rv_normalize(d);
+    const rv_f3 n = rv_dot(dir_in, h.normal) > 0.0f ? rv_neg(h.normal) : h.normal;
+    if (trace_any<kSmem>(sc, rv_add(h.pos, rv_scale(RV_EPSILON, n)), light_dir)) return splat3(0.0f);
+    return splat3(1.0f * fmaxf(0.0f, rv_dot(light_dir, n)));
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) k_modes(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    SceneViewT<kSmem> sc;
+    if constexpr (kSmem)
+    {
+        stage_scene(smem, &bar, p.scene, p.layout.bytes);
+        sc = make_view<true>(smem, p.layout);
+    }
+    else
+        sc = make_view<false>(p.scene, p.layout);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+    for (uint32_t c = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); c < p.n_chunks; c += n_warps)
+    {
+        const uint32_t slot = c * 32u + lane;
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        if (!((x < p.W_eff) && (y < p.H_eff) && ((slot >> 8) * p.nranks + p.rank < p.n_tiles))) continue;
+        const int mode = integrator_of(p, x, y);
+        if (mode == 9) continue; /* on the wavefront path */
+        uint32_t rng = rv_wang_hash(x + y * p.W) + p.frame;
+        rv_f3 sum = rv_make(0.0f, 0.0f, 0.0f);
+        for (int i = 0; i < p.aa; ++i)
+        {
+            const float jx = rv_rand(&rng);
+            const float jy = rv_rand(&rng);
+            const float cx = ((float)x + jx) * p.inv_dim_x;
+            float cy = ((float)y + jy) * p.inv_dim_y;
+            cy = 1.0f - cy;
+            rv_f3 o, d;
+            camera_ray(p, cx, cy, o, d);
+            sum = rv_add(sum, eval_mode<kSmem>(sc, mode, o, d, p.max_bounces, &rng));
+        }
+        accumulate_pixel(p, slot, rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f));
+    }
+}
+
+/* ======================================================================== */
 /* tile <-> raster                                                           */
 /* ======================================================================== */
 /* src: [n_src_ranks][n_local_padded][256] elements of `words` 32-bit words;
@@ -1053,6 +1391,25 @@ cudaError_t launch_bounce(const FrameParams& p, int b, bool smem, int grid, cuda
         k_bounce<true><<<grid, kThreads, smem_bytes_for(p, true), st>>>(p, b);
     else
         k_bounce<false><<<grid, kThreads, 0, st>>>(p, b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_modes(const FrameParams& p, bool smem, int grid, cudaStream_t st)
+{
+    if (smem)
+    {
+        static bool configured = false;
+        if (!configured)
+        {
+            cudaError_t e = cudaFuncSetAttribute(k_modes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 64 * 1024);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        k_modes<true><<<grid, kThreads, smem_bytes_for(p, true), st>>>(p);
+    }
+    else
+        k_modes<false><<<grid, kThreads, 0, st>>>(p);
     return cudaGetLastError();
 }
 

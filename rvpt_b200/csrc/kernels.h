@@ -17,6 +17,7 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
 cudaError_t launch_frame(const FrameParams& p, bool smem, int grid, cudaStream_t st);
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st);
 cudaError_t launch_bounce(const FrameParams& p, int b, bool smem, int grid, cudaStream_t st);
+cudaError_t launch_modes(const FrameParams& p, bool smem, int grid, cudaStream_t st);
 cudaError_t launch_untile(const void* src, void* dst, uint32_t words, uint32_t W, uint32_t H,
                           uint32_t tiles_x, uint32_t n_tiles, uint32_t nranks, uint32_t first_rank,
                           uint32_t n_src_ranks, uint32_t n_local_padded, cudaStream_t st);

@@ -291,8 +291,8 @@ def test_unsupported_and_error_paths(rv, builtin):
     assert e.value.code == -3  # no scene
     eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
     with pytest.raises(rv.EngineError) as e:
-        eng.render_frame(rv.default_settings(mode=3), rv.camera_data())
-    assert e.value.code == -4  # only Kajiya is on the hot path
+        eng.render_frame(rv.default_settings(mode=10), rv.camera_data())
+    assert e.value.code == -4  # integrator_Hart (sphere tracer) is out of scope
     bad = builtin.triangles.copy()
     bad["material_id"][5, 0] = 7
     with pytest.raises(rv.EngineError):
@@ -354,3 +354,34 @@ def test_cpp_headless_driver_matches_python_host(rv, builtin, tmp_path):
     for f in range(frames):  # update(): first frame is 0, then ++ (rvpt.cpp:102-111)
         eng.render_frame(rv.default_settings(frame=f), cam)
     assert np.array_equal(img, eng.read_output_rgba8()[..., :3])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+def test_other_integrators_bit_exact(rv, oracle_mod, cornell, mode):
+    """f-3: binary, color, depth, normal, Utah, AO, Appel, Whitted, Cook
+    (integrators.glsl:24-543) against the oracle, 2 frames, aa = 2."""
+    eng, ora, _ = _render_both(rv, oracle_mod, cornell, 112, 80, CORNELL_POSE, frames=2, fov=60.0,
+                               mode=mode, aa=2, max_bounces=6)
+    g, o = eng.read_accum_f32(), ora.accum
+    same = (g.view(np.uint32) == o.view(np.uint32)) | (np.isnan(g) & np.isnan(o))
+    assert same.all(), f"mode {mode}: {(~same).sum()} words differ"
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+
+
+def test_split_view_four_integrators(rv, oracle_mod, builtin):
+    """compute_pass.comp:134-144: the 4-way split picks an integrator per
+    pixel; Kajiya pixels stay on the wavefront path, the others go to k_modes."""
+    W, H = 160, 96
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+    for f in range(3):
+        rs = rv.default_settings(frame=f)
+        rs["top_left_render_mode"], rs["top_right_render_mode"] = 9, 3
+        rs["bottom_left_render_mode"], rs["bottom_right_render_mode"] = 5, 7
+        rs["split_ratio"] = (0.3, 0.6)
+        eng.render_frame(rs, cam)
+        ora.render_frame(rs, cam)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "split view")
+    assert eng.stats()["active"] == ora.active_list()  # only Kajiya pixels count as path segments

@@ -251,5 +251,28 @@ def test_running_mean_and_rgba8_store(oracle_mod, rv, builtin):
 
 def test_unsupported_integrator_is_reported(oracle_mod, rv, builtin):
     o = oracle_mod.OracleRenderer(16, 16, builtin.triangles, builtin.materials, builtin.nodes)
-    with pytest.raises(RuntimeError):
-        o.render_frame(rv.default_settings(mode=3), rv.camera_data())
+    with pytest.raises(RuntimeError):  # mode 10+: integrator_Hart, the sphere tracer (out of scope)
+        o.render_frame(rv.default_settings(mode=10), rv.camera_data())
+
+
+def test_debug_integrators_sanity(oracle_mod, rv, builtin):
+    """integrators.glsl:24-250 on the built-in scene: binary is 0/1 and marks
+    exactly the pixels whose depth is finite; color is the material albedo; the
+    normal view is 0.5*n+0.5 of a unit vector; Appel is a cosine in [0,1]."""
+    W, H = 64, 48
+    cam = rv.camera_data(translation=(0.0, 0.8, -2.5), aspect=W / H)
+
+    def render(mode):
+        o = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+        o.render_frame(rv.default_settings(mode=mode), cam)
+        return o.accum[..., :3].copy()
+
+    binary, color, depth, normal, appel = (render(m) for m in (0, 1, 2, 3, 6))
+    hit = binary[..., 0] == 1.0
+    assert set(np.unique(binary).tolist()) == {0.0, 1.0} and 0.02 < hit.mean() < 0.2
+    assert ((depth[..., 0] > 0) == hit).all()          # 1/(|d| t), t = inf on a miss
+    assert (color[hit] == 1.0).all() and not color[~hit].any()   # white Lambert (main.cpp:107)
+    n = (normal[hit] - 0.5) / 0.5
+    np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    assert not normal[~hit].any()
+    assert (appel[~hit] == 1.0).all() and appel.min() >= 0.0 and appel.max() <= 1.0
