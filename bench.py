@@ -58,7 +58,8 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=16, help="progressive frames (spp) per step")
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--aa", type=int, default=1)
-    ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell"])
+    ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell", "mesh"])
+    ap.add_argument("--mesh-tris", type=int, default=500000)
     ap.add_argument("--pose", default="default", choices=["default", "pinned"])
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
                     help="N>1: p2p = kernels store pixels into rank 0's image over NVLink (fused); "
@@ -79,6 +80,9 @@ def workload(args):
         scene = rv.builtin_scene()
         pose = (0.0, 0.0, 0.0) if args.pose == "default" else (0.0, 0.8, -2.5)
         fov = 90.0
+    elif args.scene == "mesh":
+        scene = rv.displaced_sphere_scene(args.mesh_tris)
+        pose, fov = (0.0, 1.2, -3.0), 60.0
     else:
         scene = rv.cornell_scene()
         pose, fov = (0.0, 1.2, -3.4), 60.0

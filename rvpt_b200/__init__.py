@@ -7,12 +7,13 @@ the reference's scene/camera/settings interface.
 from . import _lib  # noqa: F401
 from .engine import Engine, EngineError, build_bvh, camera_data  # noqa: F401
 from .scene import (  # noqa: F401
-    DIELECTRIC, LAMBERT, MIRROR, Scene, builtin_scene, cornell_scene, default_settings, load_obj,
+    DIELECTRIC, LAMBERT, MIRROR, Scene, builtin_scene, cornell_scene, default_settings,
+    displaced_sphere_scene, load_obj,
     make_material, make_triangles,
 )
 
 __all__ = [
     "Engine", "EngineError", "build_bvh", "camera_data", "Scene", "builtin_scene", "cornell_scene",
-    "default_settings", "load_obj", "make_material", "make_triangles", "LAMBERT", "MIRROR",
+    "default_settings", "displaced_sphere_scene", "load_obj", "make_material", "make_triangles", "LAMBERT", "MIRROR",
     "DIELECTRIC",
 ]

@@ -198,6 +198,47 @@ def cornell_scene(with_bunny: bool = True, with_blocks: bool = True) -> Scene:
     return Scene(np.concatenate(parts), mats, "cornell")
 
 
+def displaced_sphere_scene(n_triangles: int = 20000, seed: int = 1) -> Scene:
+    """A procedurally generated large mesh (SURVEY.md §8 f-1 stand-in for the
+    reference's 560 k-triangle tridel-interior-test.obj, which is not loaded by
+    main.cpp and cannot travel to the GPU box): a UV sphere of radius ~1 at
+    (0, 1, 0) with smooth radial displacement, ~n_triangles triangles, three
+    Lambert materials in latitude bands, over a large ground quad. Scenes whose
+    device blob exceeds 64 KB take the L2-resident (non-shared-memory) kernel path."""
+    nv = max(4, int(round((n_triangles / 4.0) ** 0.5)))
+    nu = 2 * nv
+    u = np.linspace(0.0, 2.0 * np.pi, nu + 1)[:-1]
+    v = np.linspace(0.0, np.pi, nv + 1)
+    uu, vv = np.meshgrid(u, v)                      # [nv+1, nu]
+    rng = np.random.default_rng(seed)
+    k = rng.uniform(1.0, 6.0, size=(6, 2))
+    ph = rng.uniform(0.0, 2.0 * np.pi, size=6)
+    r = 1.0 + sum(0.035 * np.sin(k[i, 0] * uu + ph[i]) * np.sin(k[i, 1] * vv) for i in range(6))
+    x = r * np.sin(vv) * np.cos(uu)
+    y = 1.0 + r * np.cos(vv)
+    z = r * np.sin(vv) * np.sin(uu)
+    pts = np.stack([x, y, z], axis=-1).astype(np.float32)   # [nv+1, nu, 3]
+    i0 = np.arange(nv)[:, None]
+    j0 = np.arange(nu)[None, :]
+    j1 = (j0 + 1) % nu
+    a, b, c, d = pts[i0, j0], pts[i0 + 1, j0], pts[i0 + 1, j1], pts[i0, j1]
+    band = ((i0 * 3) // nv + 0 * j0).astype(np.float32)      # material 0..2 by latitude
+    t1 = make_triangles(a.reshape(-1, 3), b.reshape(-1, 3), c.reshape(-1, 3), band.reshape(-1))
+    t2 = make_triangles(a.reshape(-1, 3), c.reshape(-1, 3), d.reshape(-1, 3), band.reshape(-1))
+    tris = np.concatenate([t1, t2])
+    # drop the degenerate triangles at the poles
+    e0 = tris["vertex1"][:, :3] - tris["vertex0"][:, :3]
+    e1 = tris["vertex2"][:, :3] - tris["vertex0"][:, :3]
+    area2 = np.linalg.norm(np.cross(e0, e1), axis=1)
+    tris = tris[area2 > 1e-12]
+    ground = _quad((-30, -0.2, -30), (-30, -0.2, 30), (30, -0.2, 30), (30, -0.2, -30), 3)
+    mats = np.concatenate([
+        make_material((0.75, 0.25, 0.2, 0)), make_material((0.8, 0.8, 0.8, 0)),
+        make_material((0.2, 0.35, 0.75, 0)), make_material((0.5, 0.5, 0.5, 0)),
+    ])
+    return Scene(np.concatenate([tris, ground]), mats, f"displaced_sphere_{len(tris) + 2}")
+
+
 def default_settings(max_bounces: int = 8, aa: int = 1, frame: int = 0, camera_mode: int = 0,
                      mode: int = 9) -> np.ndarray:
     """`RVPT::RenderSettings` defaults (src/rvpt/rvpt.h:77-89); the first

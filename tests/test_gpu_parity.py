@@ -385,3 +385,17 @@ def test_split_view_four_integrators(rv, oracle_mod, builtin):
         ora.render_frame(rs, cam)
     _assert_bit_equal(eng.read_accum_f32(), ora.accum, "split view")
     assert eng.stats()["active"] == ora.active_list()  # only Kajiya pixels count as path segments
+
+
+def test_large_scene_global_memory_path(rv, oracle_mod):
+    """f-1: a 20 k-triangle mesh (2.6 MB blob, far above the 64 KB shared-memory
+    budget) takes the L2-resident traversal path (kSmem = false) — same results."""
+    from conftest import PreparedScene
+    prep = PreparedScene(rv, rv.displaced_sphere_scene(20000))
+    assert len(prep.nodes) * 32 + len(prep.triangles) * 68 > 64 * 1024
+    eng, ora, stats = _render_both(rv, oracle_mod, prep, 192, 128, (0.0, 1.2, -3.0), frames=3, fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "large scene")
+    assert stats[-1][0]["active"] == stats[-1][1]
+    # the debug integrators use the same path
+    eng, ora, _ = _render_both(rv, oracle_mod, prep, 96, 64, (0.0, 1.2, -3.0), fov=60.0, mode=5)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "large scene, AO")
