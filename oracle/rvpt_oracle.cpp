@@ -18,7 +18,7 @@
  * mat*vec, sin/cos/tan) is fixed by include/rvpt_math.h; GLSL min/max on NaN is
  * undefined and resolved as IEEE minNum/maxNum (fminf/fmaxf).
  *
- * Build: g++ -O3 -march=native -ffp-contract=off -std=c++17 -pthread -shared -fPIC
+ * Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -std=c++17 -pthread -shared -fPIC
  */
 #include <atomic>
 #include <cstdint>

@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "librvpt_b200.so"
+import os
+
+# RVPT_B200_LIB: developer knob to A/B another build of the same library
+LIB_PATH = Path(os.environ.get("RVPT_B200_LIB") or Path(__file__).resolve().parent / "librvpt_b200.so")
 
 MAX_BOUNCE_STATS = 64
 FLAG_ACCUM_RGBA8 = 0x1

@@ -32,7 +32,7 @@ static_assert(sizeof(DevNode) == 32 && sizeof(DevTri) == 64 && sizeof(DevMateria
 
 #define RVPT_ABI_VERSION 1u
 /* scenes whose blob fits this budget are staged into shared memory per CTA */
-#define RVPT_SMEM_SCENE_LIMIT (64u * 1024u)
+#define RVPT_SMEM_SCENE_LIMIT (192u * 1024u) /* one 1024-thread CTA per SM owns the SM's shared memory */
 
 struct rvpt_b200_ctx
 {

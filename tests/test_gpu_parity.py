@@ -388,14 +388,19 @@ def test_split_view_four_integrators(rv, oracle_mod, builtin):
 
 
 def test_large_scene_global_memory_path(rv, oracle_mod):
-    """f-1: a 20 k-triangle mesh (2.6 MB blob, far above the 64 KB shared-memory
+    """f-1: a 20 k-triangle mesh (2.6 MB blob, far above the 192 KB shared-memory
     budget) takes the L2-resident traversal path (kSmem = false) — same results."""
     from conftest import PreparedScene
     prep = PreparedScene(rv, rv.displaced_sphere_scene(20000))
-    assert len(prep.nodes) * 32 + len(prep.triangles) * 68 > 64 * 1024
+    assert len(prep.nodes) * 32 + len(prep.triangles) * 68 > 192 * 1024
     eng, ora, stats = _render_both(rv, oracle_mod, prep, 192, 128, (0.0, 1.2, -3.0), frames=3, fov=60.0)
     _assert_bit_equal(eng.read_accum_f32(), ora.accum, "large scene")
     assert stats[-1][0]["active"] == stats[-1][1]
     # the debug integrators use the same path
     eng, ora, _ = _render_both(rv, oracle_mod, prep, 96, 64, (0.0, 1.2, -3.0), fov=60.0, mode=5)
     _assert_bit_equal(eng.read_accum_f32(), ora.accum, "large scene, AO")
+    # a medium scene (~900 triangles, ~150-190 KB with the origin-relative copies) still fits
+    # the shared-memory budget of the one-CTA-per-SM kernel
+    mid = PreparedScene(rv, rv.displaced_sphere_scene(900))
+    eng, ora, _ = _render_both(rv, oracle_mod, mid, 128, 96, (0.0, 1.2, -3.0), frames=2, fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "medium scene in shared memory")
