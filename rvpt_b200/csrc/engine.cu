@@ -9,6 +9,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -42,6 +43,8 @@ struct rvpt_b200_ctx
     uint32_t rank = 0, nranks = 1;
     uint32_t n_local_tiles = 0, n_local_padded = 0;
     int num_sms = 0;
+    int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
+    int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
     int grid_frame = 0, grid_primary = 0, grid_bounce = 0;
     uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
     uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
@@ -382,6 +385,35 @@ int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
     return 0;
 }
 
+/* A scene too large for shared memory is traversed out of L2 (kSmem = false): pin its blob
+ * there with an access-policy window so the path-state streams (hundreds of MB per frame)
+ * do not evict it. Best effort: failures only cost performance. */
+void apply_scene_l2_policy(rvpt_b200_ctx* ctx)
+{
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    if (!ctx->scene_smem && ctx->l2_persist_max > 0)
+    {
+        const size_t want = std::min<size_t>(ctx->layout.bytes, (size_t)ctx->l2_persist_max);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        attr.accessPolicyWindow.base_ptr = ctx->d_scene;
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->layout.bytes, (size_t)ctx->l2_window_max);
+        attr.accessPolicyWindow.hitRatio =
+            ctx->layout.bytes <= want ? 1.0f : (float)want / (float)ctx->layout.bytes;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    else
+    {
+        attr.accessPolicyWindow.num_bytes = 0; /* disables the window */
+        attr.accessPolicyWindow.hitRatio = 0.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError(); /* best effort */
+}
+
 int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
 {
     SceneLayout L{};
@@ -450,6 +482,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
         ctx->grid_bounce = ctx->num_sms * occ_b;
     }
     ctx->have_scene = true;
+    apply_scene_l2_policy(ctx);
     return 0;
 }
 
@@ -505,6 +538,8 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
                     device, prop.major, prop.minor);
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->l2_persist_max = prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->scene_copied, cudaEventDisableTiming));
     ctx->stream = ctx->own_stream;
@@ -553,6 +588,7 @@ extern "C" int rvpt_b200_set_stream(rvpt_b200_ctx* ctx, void* cuda_stream)
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (ctx->have_scene) apply_scene_l2_policy(ctx);
     return 0;
 }
 

@@ -499,10 +499,12 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
     if (alive)
     {
         const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
-        q.q0[i] = make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot));
-        q.q1[i] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.rng));
-        q.q2[i] = make_float4(s.thr.x, s.thr.y, s.thr.z, 0.0f);
-        q.q3[i] = make_float4(s.col.x, s.col.y, s.col.z, 0.0f);
+        /* path state is written once and read once: streaming stores / loads (evict-first)
+         * keep L2 for the accumulation image and, for large scenes, the BVH */
+        __stcs(&q.q0[i], make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot)));
+        __stcs(&q.q1[i], make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.rng)));
+        __stcs(&q.q2[i], make_float4(s.thr.x, s.thr.y, s.thr.z, 0.0f));
+        __stcs(&q.q3[i], make_float4(s.col.x, s.col.y, s.col.z, 0.0f));
     }
     (void)p;
 }
@@ -673,10 +675,10 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
 __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathState& s,
                                           uint32_t& slot)
 {
-    const float4 a0 = q.q0[i];
-    const float4 a1 = q.q1[i];
-    const float4 a2 = q.q2[i];
-    const float4 a3 = q.q3[i];
+    const float4 a0 = __ldcs(&q.q0[i]);
+    const float4 a1 = __ldcs(&q.q1[i]);
+    const float4 a2 = __ldcs(&q.q2[i]);
+    const float4 a3 = __ldcs(&q.q3[i]);
     s.o = rv_make(a0.x, a0.y, a0.z);
     slot = __float_as_uint(a0.w);
     s.d = rv_make(a1.x, a1.y, a1.z);
