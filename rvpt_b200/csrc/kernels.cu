@@ -287,7 +287,16 @@ __device__ __forceinline__ void slot_to_xy(const FrameParams& p, uint32_t slot, 
 
 /* compute_pass.comp:146-148, 162-166: running mean with the previous image and
  * the two rgba8 stores, for the frame's mean sample `sampled`. */
-__device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t slot, rv_f3 sampled)
+/* rv_unorm8_store on the device: saturate (NaN -> 0) and round-to-nearest-even
+ * conversion are single instructions; same codes as the header's formulation. */
+__device__ __forceinline__ unsigned char dev_unorm8(float x)
+{
+    return (unsigned char)__float2uint_rn(__saturatef(x) * 255.0f);
+}
+
+/* `raster` = y*W + x when the caller already knows the pixel, 0xFFFFFFFF otherwise */
+__device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t slot, rv_f3 sampled,
+                                                 uint32_t raster = 0xFFFFFFFFu)
 {
     rv_f3 prev;
     const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
@@ -305,18 +314,20 @@ __device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t 
     const rv_f3 acc = rv_make((temporal.x * p.frame_f + sampled.x) * p.inv_frame1,
                               (temporal.y * p.frame_f + sampled.y) * p.inv_frame1,
                               (temporal.z * p.frame_f + sampled.z) * p.inv_frame1);
-    const uchar4 q = make_uchar4((unsigned char)rv_unorm8_store(acc.x),
-                                 (unsigned char)rv_unorm8_store(acc.y),
-                                 (unsigned char)rv_unorm8_store(acc.z), 0);
+    const uchar4 q = make_uchar4(dev_unorm8(acc.x), dev_unorm8(acc.y), dev_unorm8(acc.z), 0);
     if (u8)
         p.accum_u8[slot] = q;
     else
         p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
     if (p.out_raster)
     {
-        uint32_t x, y;
-        slot_to_xy(p, slot, x, y);
-        p.out_raster[(size_t)y * p.W + x] = q;
+        if (raster == 0xFFFFFFFFu)
+        {
+            uint32_t x, y;
+            slot_to_xy(p, slot, x, y);
+            raster = y * p.W + x;
+        }
+        p.out_raster[raster] = q;
     }
     else
         p.out_tiles[slot] = q;
@@ -351,7 +362,7 @@ __device__ __forceinline__ void prefetch_prev(const FrameParams& p, uint32_t slo
 }
 
 __device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slot, rv_f3 s,
-                                              uint32_t rng)
+                                              uint32_t rng, uint32_t raster = 0xFFFFFFFFu)
 {
     /* sampled = vec3(0); sampled += eval_integrator(...) */
     rv_f3 sum;
@@ -370,7 +381,7 @@ __device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slo
     /* sampled /= aa ; x / 1.0f == x exactly, so the common aa = 1 case skips three divisions */
     const rv_f3 sampled =
         p.aa == 1 ? sum : rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f);
-    accumulate_pixel(p, slot, sampled);
+    accumulate_pixel(p, slot, sampled, raster);
 }
 
 /* ---- one iteration of integrator_Kajiya's loop (integrators.glsl:574-671) -- */
@@ -662,7 +673,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
                     sample = rv_make(0.0f, 0.0f, 0.0f);
                 }
             }
-            if (!alive) finish_sample(p, slot, sample, s.rng);
+            if (!alive) finish_sample(p, slot, sample, s.rng, y * p.W + x);
         }
         if (p.max_bounces > 0)
             traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
@@ -1188,7 +1199,7 @@ __global__ void __launch_bounds__(kThreads) k_modes(const FrameParams p)
             camera_ray(p, cx, cy, o, d);
             sum = rv_add(sum, eval_mode<kSmem>(sc, mode, o, d, p.max_bounces, &rng));
         }
-        accumulate_pixel(p, slot, rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f));
+        accumulate_pixel(p, slot, rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f), y * p.W + x);
     }
 }
 
@@ -1268,8 +1279,7 @@ __global__ void k_f32_to_u8(const float4* __restrict__ src, uchar4* __restrict__
          e += (uint64_t)gridDim.x * blockDim.x)
     {
         const float4 a = src[e];
-        dst[e] = make_uchar4((unsigned char)rv_unorm8_store(a.x), (unsigned char)rv_unorm8_store(a.y),
-                             (unsigned char)rv_unorm8_store(a.z), 0);
+        dst[e] = make_uchar4(dev_unorm8(a.x), dev_unorm8(a.y), dev_unorm8(a.z), 0);
     }
 }
 
