@@ -438,3 +438,33 @@ def test_c4_full_size_4k_partition(rv, oracle_mod, builtin):
     for f in range(2):
         ora.render_frame(rv.default_settings(frame=f), cam, y0, y1)
     _assert_bit_equal(want[y0:y1], ora.accum[y0:y1], "4K rows vs oracle")
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (16, 16), (17, 33)])
+def test_tiny_and_ragged_images(rv, oracle_mod, builtin, size):
+    """Edge sizes: a single pixel, less than one tile, exactly one tile, ragged."""
+    W, H = size
+    eng, ora, stats = _render_both(rv, oracle_mod, builtin, W, H, DEFAULT_POSE, frames=2)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"{W}x{H}")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    assert stats[-1][0]["samples"] == W * H
+
+
+def test_more_ranks_than_tiles(rv, builtin):
+    """A rank that owns no tile renders nothing and reads back zeros."""
+    W, H = 24, 16  # 2 tiles
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    full = rv.Engine(W, H)
+    full.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    full.render_frame(rv.default_settings(), cam)
+    acc = np.zeros((H, W, 4), np.float32)
+    for r in range(4):
+        eng = rv.Engine(W, H, rank=r, nranks=4)
+        eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+        eng.render_frame(rv.default_settings(), cam)
+        a = eng.read_accum_f32()
+        if r >= 2:
+            assert not a.any() and eng.stats()["samples"] == 0
+        acc += a
+        eng.close()
+    _assert_bit_equal(acc, full.read_accum_f32(), "4 ranks, 2 tiles")
