@@ -135,6 +135,10 @@ typedef struct rvpt_b200_stats
  * instead of the single persistent cooperative kernel per frame. Same results;
  * used for per-wave profiling and as a cross-check of the fused kernel. */
 #define RVPT_B200_FLAG_UNFUSED 0x8u
+/* Do not build the per-CTA direction-octant copies of the BVH nodes (the slab
+ * test then uses the reference's per-axis min/max form for every ray). Same
+ * results; for A/B measurements. */
+#define RVPT_B200_FLAG_NO_OCTANTS 0x10u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 
@@ -218,6 +222,15 @@ typedef struct rvpt_b200_kernel_times
 } rvpt_b200_kernel_times;
 RVPT_API int rvpt_b200_set_profiling(rvpt_b200_ctx* ctx, int enabled);
 RVPT_API int rvpt_b200_get_kernel_times(rvpt_b200_ctx* ctx, rvpt_b200_kernel_times* out);
+
+/* Per-CTA phase time stamps (%globaltimer, ns) of the most recent frame kernel:
+ * out[cta * n_slots + k]; k = 0 kernel entry, 1 scene staged, 2 primary wave
+ * done (first warp of the CTA), then for every bounce wave b: 2b+1 = past the
+ * grid barrier that precedes it, 2b+2 = wave done. 0 = phase not reached.
+ * For locating idle time inside the persistent kernel; off by default. */
+RVPT_API int rvpt_b200_set_timeline(rvpt_b200_ctx* ctx, int enabled);
+RVPT_API int rvpt_b200_get_timeline(rvpt_b200_ctx* ctx, uint64_t* out, size_t capacity,
+                                    uint32_t* n_ctas, uint32_t* n_slots);
 
 /* ------------------------------------------------------------------------ */
 /* Device-side tile buffers, for the multi-GPU gather (NCCL runs in the      */

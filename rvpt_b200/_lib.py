@@ -18,6 +18,7 @@ FLAG_ACCUM_RGBA8 = 0x1
 FLAG_REFERENCE_DISPATCH = 0x2
 FLAG_BRUTE_FORCE = 0x4
 FLAG_UNFUSED = 0x8
+FLAG_NO_OCTANTS = 0x10
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -69,6 +70,9 @@ SIGNATURES = {
     "rvpt_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "rvpt_b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rvpt_b200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTimes)]),
+    "rvpt_b200_set_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "rvpt_b200_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint32)]),
     "rvpt_b200_get_tile_info": (C.c_int, [C.c_void_p, C.POINTER(TileInfo)]),
     "rvpt_b200_set_external_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvpt_b200_untile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),

@@ -13,6 +13,7 @@
 #define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
+#define RVPT_TIMELINE_SLOTS 16u     /* per-CTA phase stamps of the last frame kernel */
 
 /*
  * BVH node, 32 B (two 128-bit loads). Nodes are re-laid-out in the order the
@@ -156,6 +157,7 @@ struct FrameParams
     uint32_t wave_set;            /* launch sequence parity */
     uint32_t stats_set;           /* frame sequence parity */
     uint32_t tail_threshold;      /* waves this small finish inside their threads */
+    unsigned long long* timeline; /* optional [n_ctas][RVPT_TIMELINE_SLOTS] globaltimer stamps */
 };
 
 #endif

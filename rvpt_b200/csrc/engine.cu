@@ -33,7 +33,7 @@ static_assert(sizeof(DevNode) == 32 && sizeof(DevTri) == 64 && sizeof(DevMateria
 
 #define RVPT_ABI_VERSION 1u
 /* scenes whose blob fits this budget are staged into shared memory per CTA */
-#define RVPT_SMEM_SCENE_LIMIT (192u * 1024u) /* one 1024-thread CTA per SM owns the SM's shared memory */
+#define RVPT_SMEM_SCENE_LIMIT (224u * 1024u) /* one 1024-thread CTA per SM owns the SM's shared memory (227 KB opt-in max) */
 
 struct rvpt_b200_ctx
 {
@@ -59,6 +59,7 @@ struct rvpt_b200_ctx
     cudaEvent_t scene_copied = nullptr;
     SceneLayout layout{};
     bool scene_smem = false;
+    bool scene_oct = false; /* direction-octant node copies fit next to the blob */
     bool have_scene = false;
 
     /* frame buffers (tile layout) */
@@ -78,6 +79,10 @@ struct rvpt_b200_ctx
     int last_aa = 0;
     uint32_t last_launches = 0;
     uint32_t last_stats_set = 0;
+
+    /* per-CTA phase stamps of the last frame kernel (set_timeline) */
+    unsigned long long* d_timeline = nullptr;
+    int timeline_ctas = 0;
 
     /* per-kernel timing */
     bool profiling = false;
@@ -233,6 +238,7 @@ struct ScopedTimer
 
 struct PackedScene
 {
+    bool bounds_ordered = true; /* every node has min <= max on every axis (no NaN) */
     std::vector<DevNode> nodes;
     std::vector<DevTri> tris;
     std::vector<uint32_t> meta;
@@ -345,6 +351,9 @@ int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
         d.bmax_y = s.bounds[3], d.bmin_z = s.bounds[4], d.bmax_z = s.bounds[5];
         d.skip = RVPT_NODE_END;
         d.leaf_first = RVPT_NODE_INNER;
+        /* the octant copies assume ordered bounds; anything else keeps the min/max walk */
+        if (!(d.bmin_x <= d.bmax_x && d.bmin_y <= d.bmax_y && d.bmin_z <= d.bmax_z))
+            out.bounds_ordered = false;
         if (s.primitive_count > 0)
         {
             if ((size_t)s.first_child_or_primitive + s.primitive_count > n_tris)
@@ -463,16 +472,21 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
                        ctx->stream));
     CU(cudaEventRecord(ctx->scene_copied, ctx->stream));
 
+    const bool oct = !(ctx->flags & RVPT_B200_FLAG_NO_OCTANTS) && ps.bounds_ordered &&
+                     rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris, true) <= RVPT_SMEM_SCENE_LIMIT;
     const bool same_shape = ctx->have_scene && L.bytes == ctx->layout.bytes &&
-                            L.n_nodes == ctx->layout.n_nodes && L.n_tris == ctx->layout.n_tris;
+                            L.n_nodes == ctx->layout.n_nodes && L.n_tris == ctx->layout.n_tris &&
+                            oct == ctx->scene_oct;
     ctx->layout = L;
+    ctx->scene_oct = oct;
     if (!same_shape)
     {
         ctx->scene_smem =
-            rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris) <= RVPT_SMEM_SCENE_LIMIT;
+            rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris, false) <= RVPT_SMEM_SCENE_LIMIT;
         int occ_f = 0, occ_p = 0, occ_b = 0;
         if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
-        CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, L.bytes, L.n_nodes, L.n_tris));
+        CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, ctx->scene_oct, L.bytes, L.n_nodes,
+                           L.n_tris));
         if (occ_f < 1 || occ_p < 1 || occ_b < 1)
             return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)",
                         occ_f, occ_p, occ_b);
@@ -516,7 +530,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (width == 0 || height == 0 || width > 65536 || height > 65536)
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
-                  RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED))
+                  RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     ctx->device = device;
     ctx->W = width;
@@ -555,6 +569,7 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
         cudaStreamSynchronize(ctx->stream);
         if (ctx->peer_out_raster) cudaIpcCloseMemHandle(ctx->peer_out_raster);
         free_frame_buffers(ctx);
+        cudaFree(ctx->d_timeline);
         cudaFree(ctx->d_scene);
         if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
         if (ctx->scene_copied) cudaEventDestroy(ctx->scene_copied);
@@ -692,6 +707,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.out_raster = ctx->peer_out_raster ? ctx->peer_out_raster : ctx->d_out_raster;
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
+    p.timeline = ctx->d_timeline;
 
     p.stats_set = ctx->frame_seq & 1u;
     const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;
@@ -706,7 +722,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
         if (!unfused)
         {
             ScopedTimer tm(ctx, 0);
-            CU(rvpt::launch_frame(p, ctx->scene_smem, ctx->grid_frame, ctx->stream));
+            CU(rvpt::launch_frame(p, ctx->scene_smem, ctx->scene_oct, ctx->grid_frame, ctx->stream));
             ++launches;
         }
         else
@@ -900,6 +916,42 @@ extern "C" int rvpt_b200_get_kernel_times(rvpt_b200_ctx* ctx, rvpt_b200_kernel_t
         ctx->event_pool.push_back(t);
     }
     ctx->timed.clear();
+    return 0;
+}
+
+extern "C" int rvpt_b200_set_timeline(rvpt_b200_ctx* ctx, int enabled)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, RVPT_B200_ENOSCENE, "set_timeline before upload_scene");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_timeline);
+    ctx->d_timeline = nullptr;
+    ctx->timeline_ctas = 0;
+    if (enabled)
+    {
+        const size_t bytes = (size_t)ctx->grid_frame * RVPT_TIMELINE_SLOTS * sizeof(unsigned long long);
+        CU(cudaMalloc(&ctx->d_timeline, bytes));
+        CU(cudaMemset(ctx->d_timeline, 0, bytes));
+        ctx->timeline_ctas = ctx->grid_frame;
+    }
+    return 0;
+}
+
+extern "C" int rvpt_b200_get_timeline(rvpt_b200_ctx* ctx, uint64_t* out, size_t capacity,
+                                      uint32_t* n_ctas, uint32_t* n_slots)
+{
+    if (!ctx || !n_ctas || !n_slots) return RVPT_B200_EINVAL;
+    *n_ctas = (uint32_t)ctx->timeline_ctas;
+    *n_slots = RVPT_TIMELINE_SLOTS;
+    if (!ctx->d_timeline || !out) return 0;
+    const size_t n = (size_t)ctx->timeline_ctas * RVPT_TIMELINE_SLOTS;
+    if (capacity < n) return fail(ctx, RVPT_B200_EINVAL, "timeline needs %zu entries", n);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, ctx->d_timeline, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    /* stamps of phases a later frame does not reach must not survive */
+    CU(cudaMemset(ctx->d_timeline, 0, n * sizeof(uint64_t)));
     return 0;
 }
 

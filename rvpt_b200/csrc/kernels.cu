@@ -138,6 +138,12 @@ struct SceneViewT
      * identical for every primary ray of a pinhole or spherical camera. */
     addr_t rel_nodes;
     addr_t rel_num;
+    /* kOct only: eight copies of the node array, one per ray-direction octant, with
+     * each axis' two bounds stored (near, far) for that octant — and eight more relative
+     * to the camera origin for the primary wave. oct_stride = n_nodes * 32 bytes. */
+    addr_t oct_nodes;
+    addr_t oct_rel_nodes;
+    uint32_t oct_stride;
 };
 
 template <bool kSmem, typename A>
@@ -184,20 +190,65 @@ __device__ __forceinline__ SceneViewT<kSmem> make_view(const unsigned char* base
     v.mats = b + L.off_mats;
     v.rel_nodes = 0;
     v.rel_num = 0;
+    v.oct_nodes = 0;
+    v.oct_rel_nodes = 0;
+    v.oct_stride = 0;
     return v;
 }
 
 /* ---- nearest hit: stackless walk in the reference's visiting order ------- */
 
+/* Leaf: intersect_triangle_fast (intersection.glsl:267-323) on the precomputed
+ * records of one leaf; the early-out after the plane test is value-neutral
+ * because the acceptance test is a pure conjunction. */
 template <bool kSmem, bool kRel>
-__device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d,
-                                              float& best_t, uint32_t& best_tri)
+__device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d, uint32_t i,
+                                          float& best_t, uint32_t& best_tri)
 {
-    const typename SceneViewT<kSmem>::addr_t nodes = kRel ? sc.rel_nodes : sc.nodes;
-    /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
-    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
-    best_t = RV_INF;
-    best_tri = 0xFFFFFFFFu;
+    uint32_t m;
+    do
+    {
+        const float4 A = ld_f4<kSmem>(sc.tris, 4 * i + 0);
+        const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
+        m = ld_u32<kSmem>(sc.meta, i);
+        const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, i))
+                               : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
+                                        rv_make(B.x, B.y, B.z));
+        const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
+        const float t = num / den;
+        if (0.0f < t && t < best_t)
+        {
+            const float4 C = ld_f4<kSmem>(sc.tris, 4 * i + 2);
+            const float4 D = ld_f4<kSmem>(sc.tris, 4 * i + 3);
+            const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
+            const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
+            const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
+            const float by = rv_dot(p0, rv_make(D.x, D.y, D.z));
+            const float m0 = B.w * bx, m1 = C.w * by; /* A00*bx + A10*by */
+            const float m2 = C.w * bx, m3 = D.w * by; /* A01*bx + A11*by */
+            const float u = A.w * (m0 + m1);
+            const float v = A.w * (m2 + m3);
+            if (0.0f < u && 0.0f < v && u + v < 1.0f)
+            {
+                best_t = t;
+                best_tri = i;
+            }
+        }
+        ++i;
+    } while (!(m & RVPT_TRI_LAST));
+}
+
+/* The walk. kSorted: `nodes` is the copy for this ray's direction octant, whose
+ * records hold (near, far) per axis, so the slab test needs no per-axis min/max:
+ * for a finite non-zero invdir and bmin <= bmax, rounding is monotonic and
+ * min((bmin-o)*inv, (bmax-o)*inv) IS the product with the near bound. max/min over
+ * the three axes, 0 and closest_t are order-independent for non-NaN values. */
+template <bool kSmem, bool kRel, bool kSorted>
+__device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
+                                             const typename SceneViewT<kSmem>::addr_t nodes, rv_f3 o,
+                                             rv_f3 d, float ix, float iy, float iz, float& best_t,
+                                             uint32_t& best_tri)
+{
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
@@ -216,51 +267,26 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
             fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
             fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
         }
-        float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
-        float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
-        t0 = fmaxf(t0, 0.0f);
-        t1 = fminf(t1, best_t);
+        float t0, t1;
+        if (kSorted)
+        {
+            t0 = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+            t1 = fminf(fminf(fx, fy), fminf(fz, best_t));
+        }
+        else
+        {
+            t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+            t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+            t0 = fmaxf(t0, 0.0f);
+            t1 = fminf(t1, best_t);
+        }
         const uint32_t skip = __float_as_uint(n1.z);
         const uint32_t leaf = __float_as_uint(n1.w);
         if (t1 >= t0)
         {
             if (leaf != RVPT_NODE_INNER)
             {
-                uint32_t i = leaf;
-                uint32_t m;
-                do
-                {
-                    /* intersect_triangle_fast (intersection.glsl:267-323) on the
-                     * precomputed record; the early-out is value-neutral because
-                     * the acceptance test is a pure conjunction. */
-                    const float4 A = ld_f4<kSmem>(sc.tris, 4 * i + 0);
-                    const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
-                    m = ld_u32<kSmem>(sc.meta, i);
-                    const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, i))
-                                           : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
-                                                    rv_make(B.x, B.y, B.z));
-                    const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
-                    const float t = num / den;
-                    if (0.0f < t && t < best_t)
-                    {
-                        const float4 C = ld_f4<kSmem>(sc.tris, 4 * i + 2);
-                        const float4 D = ld_f4<kSmem>(sc.tris, 4 * i + 3);
-                        const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
-                        const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
-                        const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
-                        const float by = rv_dot(p0, rv_make(D.x, D.y, D.z));
-                        const float m0 = B.w * bx, m1 = C.w * by; /* A00*bx + A10*by */
-                        const float m2 = C.w * bx, m3 = D.w * by; /* A01*bx + A11*by */
-                        const float u = A.w * (m0 + m1);
-                        const float v = A.w * (m2 + m3);
-                        if (0.0f < u && 0.0f < v && u + v < 1.0f)
-                        {
-                            best_t = t;
-                            best_tri = i;
-                        }
-                    }
-                    ++i;
-                } while (!(m & RVPT_TRI_LAST));
+                test_leaf<kSmem, kRel>(sc, o, d, leaf, best_t, best_tri);
                 node = skip;
             }
             else
@@ -269,6 +295,40 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
         else
             node = skip;
     }
+}
+
+template <bool kSmem, bool kRel, bool kOct>
+__device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d,
+                                              float& best_t, uint32_t& best_tri)
+{
+    /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    best_t = RV_INF;
+    best_tri = 0xFFFFFFFFu;
+    if constexpr (kOct)
+    {
+        /* The sorted copies are exact only while no product can be NaN on one side
+         * of a slab alone, i.e. every invdir component is finite and non-zero; the
+         * (practically never taken) other case walks the plain copy with the
+         * reference's min/max formulation. */
+        const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
+        const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
+        if (lo > 0.0f && hi < RV_INF)
+        {
+            const uint32_t oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
+                                 ((__float_as_uint(iz) >> 31) << 2);
+            uint32_t base = (uint32_t)(kRel ? sc.oct_rel_nodes : sc.oct_nodes) + oct * sc.oct_stride;
+            /* opaque to ptxas, which otherwise re-derives this address (shared window base,
+             * constant-bank loads, octant bits) inside the node loop to save a register */
+            asm volatile("" : "+r"(base));
+            walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+        }
+        else
+            walk_nearest<kSmem, false, false>(sc, sc.nodes, o, d, ix, iy, iz, best_t, best_tri);
+    }
+    else
+        walk_nearest<kSmem, kRel, false>(sc, kRel ? sc.rel_nodes : sc.nodes, o, d, ix, iy, iz, best_t,
+                                         best_tri);
 }
 
 /* ---- slot <-> pixel ------------------------------------------------------- */
@@ -394,12 +454,12 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
-template <bool kSmem, bool kRel>
+template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
-    trace_nearest<kSmem, kRel>(sc, s.o, s.d, t, tri);
+    trace_nearest<kSmem, kRel, kOct>(sc, s.o, s.d, t, tri);
 
     if (tri == 0xFFFFFFFFu)
     {
@@ -588,7 +648,7 @@ __device__ __forceinline__ void clear_next_counters(const FrameParams& p)
 }
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
-template <bool kSmem, bool kRel>
+template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneViewT<kSmem>& sc)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
@@ -666,7 +726,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
             rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
             if (p.max_bounces > 0)
             {
-                alive = kajiya_step<kSmem, kRel>(sc, s, sample);
+                alive = kajiya_step<kSmem, kRel, kOct>(sc, s, sample);
                 if (alive && p.max_bounces == 1)
                 {
                     alive = false; /* :674-675 ran out of iterations */
@@ -713,7 +773,7 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
  */
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_IN_THREAD 2u
-template <bool kSmem>
+template <bool kSmem, bool kOct>
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
                                              uint32_t count, uint32_t mode)
 {
@@ -765,7 +825,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             rv_f3 sample;
             for (int k = b;; ++k)
             {
-                alive = kajiya_step<kSmem, false>(sc, s, sample);
+                alive = kajiya_step<kSmem, false, kOct>(sc, s, sample);
                 if (alive && k == p.max_bounces - 1)
                 {
                     alive = false; /* integrators.glsl:674-675: col is discarded */
@@ -781,54 +841,119 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
 }
 
 /* ======================================================================== */
+/* scene set-up shared by the frame kernels                                   */
+/* ======================================================================== */
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+/* optional per-CTA phase stamps (rvpt_b200_set_timeline): slot k of this CTA */
+__device__ __forceinline__ void stamp(const FrameParams& p, uint32_t k)
+{
+    if (p.timeline && threadIdx.x == 0 && k < RVPT_TIMELINE_SLOTS)
+        p.timeline[blockIdx.x * RVPT_TIMELINE_SLOTS + k] = global_ns();
+}
+
+/* Stage the blob with TMA and derive the per-frame copies every ray of the CTA
+ * shares:
+ *   kRel  origin-relative data for the primary wave (the first subtraction of
+ *         intersect_aabb and the numerator of the plane test are the same for all
+ *         rays of a pinhole / spherical camera: cam.matrix[3].xyz, camera.glsl:46,94)
+ *   kOct  eight direction-octant copies of the nodes with (near, far) bounds, absolute
+ *         for bounce rays and origin-relative for primary rays. */
+template <bool kSmem, bool kRel, bool kOct>
+__device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, unsigned char* smem,
+                                                         uint64_t* bar)
+{
+    SceneViewT<kSmem> sc;
+    if constexpr (kSmem)
+    {
+        stage_scene(smem, bar, p.scene, p.layout.bytes);
+        sc = make_view<true>(smem, p.layout);
+        unsigned char* extra = smem + p.layout.bytes;
+        const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
+        const uint32_t n_nodes = p.layout.n_nodes;
+        if constexpr (kRel)
+        {
+            float* rel_num = reinterpret_cast<float*>(extra);
+            extra += ((size_t)p.layout.n_tris * 4u + 15u) & ~(size_t)15u;
+            for (uint32_t i = threadIdx.x; i < p.layout.n_tris; i += blockDim.x)
+            {
+                const float4 A = ld_f4<true>(sc.tris, 4 * i), B = ld_f4<true>(sc.tris, 4 * i + 1);
+                rel_num[i] = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
+            }
+            sc.rel_num = smem_u32(rel_num);
+        }
+        if constexpr (kOct)
+        {
+            static_assert(kWarpsPerCta % 8 == 0, "one warp group per octant");
+            float4* oct = reinterpret_cast<float4*>(extra);
+            float4* oct_rel = oct + 16 * (size_t)n_nodes;
+            const uint32_t w = threadIdx.x >> 5, k = w & 7u;
+            float4* dst = oct + 2 * (size_t)n_nodes * k;
+            float4* dst_rel = oct_rel + 2 * (size_t)n_nodes * k;
+            for (uint32_t i = (w >> 3) * 32u + (threadIdx.x & 31u); i < n_nodes; i += (kWarpsPerCta / 8) * 32u)
+            {
+                const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
+                const float ax = (k & 1u) ? n0.y : n0.x, bx = (k & 1u) ? n0.x : n0.y;
+                const float ay = (k & 2u) ? n0.w : n0.z, by = (k & 2u) ? n0.z : n0.w;
+                const float az = (k & 4u) ? n1.y : n1.x, bz = (k & 4u) ? n1.x : n1.y;
+                dst[2 * i] = make_float4(ax, bx, ay, by);
+                dst[2 * i + 1] = make_float4(az, bz, n1.z, n1.w);
+                if constexpr (kRel)
+                {
+                    dst_rel[2 * i] = make_float4(ax - o.x, bx - o.x, ay - o.y, by - o.y);
+                    dst_rel[2 * i + 1] = make_float4(az - o.z, bz - o.z, n1.z, n1.w);
+                }
+            }
+            sc.oct_nodes = smem_u32(oct);
+            sc.oct_rel_nodes = smem_u32(oct_rel);
+            sc.oct_stride = n_nodes * 32u;
+        }
+        else if constexpr (kRel)
+        {
+            float4* rel_nodes = reinterpret_cast<float4*>(extra);
+            for (uint32_t i = threadIdx.x; i < n_nodes; i += blockDim.x)
+            {
+                const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
+                rel_nodes[2 * i] = make_float4(n0.x - o.x, n0.y - o.x, n0.z - o.y, n0.w - o.y);
+                rel_nodes[2 * i + 1] = make_float4(n1.x - o.z, n1.y - o.z, n1.z, n1.w);
+            }
+            sc.rel_nodes = smem_u32(rel_nodes);
+        }
+        if constexpr (kRel || kOct) __syncthreads();
+    }
+    else
+        sc = make_view<false>(p.scene, p.layout);
+    return sc;
+}
+
+/* ======================================================================== */
 /* k_frame: the whole frame (one aa pass) in ONE persistent cooperative launch */
 /* ======================================================================== */
-template <bool kSmem, bool kRel>
+template <bool kSmem, bool kRel, bool kOct>
 __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 
+    stamp(p, 0);
     clear_next_counters(p);
-    SceneViewT<kSmem> sc;
-    if constexpr (kSmem)
-    {
-        stage_scene(smem, &bar, p.scene, p.layout.bytes);
-        sc = make_view<true>(smem, p.layout);
-        if constexpr (kRel)
-        {
-            /* origin-relative copies for the primary wave (same subtractions /
-             * dot product every primary ray would do: cam.matrix[3].xyz is the
-             * origin of all pinhole and spherical camera rays, camera.glsl:46,94) */
-            float4* rel_nodes = reinterpret_cast<float4*>(smem + p.layout.bytes);
-            float* rel_num = reinterpret_cast<float*>(rel_nodes + 2 * p.layout.n_nodes);
-            const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
-            for (uint32_t i = threadIdx.x; i < p.layout.n_nodes; i += blockDim.x)
-            {
-                const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
-                rel_nodes[2 * i] = make_float4(n0.x - o.x, n0.y - o.x, n0.z - o.y, n0.w - o.y);
-                rel_nodes[2 * i + 1] = make_float4(n1.x - o.z, n1.y - o.z, n1.z, n1.w);
-            }
-            for (uint32_t i = threadIdx.x; i < p.layout.n_tris; i += blockDim.x)
-            {
-                const float4 A = ld_f4<true>(sc.tris, 4 * i), B = ld_f4<true>(sc.tris, 4 * i + 1);
-                rel_num[i] = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
-            }
-            sc.rel_nodes = smem_u32(rel_nodes);
-            sc.rel_num = smem_u32(rel_num);
-            __syncthreads();
-        }
-    }
-    else
-        sc = make_view<false>(p.scene, p.layout);
+    const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);
+    stamp(p, 1);
 
-    primary_phase<kSmem, kRel>(p, sc);
+    primary_phase<kSmem, kRel, kOct>(p, sc);
+    stamp(p, 2);
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     for (int b = 1; b < p.max_bounces; ++b)
     {
         grid.sync(); /* wave b-1 is complete: its survivor count is final */
+        stamp(p, 2 * b + 1);
         const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&wc.qcount[b - 1]);
         if (count == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
@@ -836,10 +961,12 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         if (count <= p.tail_threshold)
         {
-            bounce_phase<kSmem>(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
+            bounce_phase<kSmem, kOct>(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
+            stamp(p, 2 * b + 2);
             break;
         }
-        bounce_phase<kSmem>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+        bounce_phase<kSmem, kOct>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+        stamp(p, 2 * b + 2);
     }
 }
 
@@ -860,7 +987,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     }
     else
         sc = make_view<false>(p.scene, p.layout);
-    primary_phase<kSmem, false>(p, sc);
+    primary_phase<kSmem, false, false>(p, sc);
 }
 
 template <bool kSmem>
@@ -884,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     else
         sc = make_view<false>(p.scene, p.layout);
     const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-    bounce_phase<kSmem>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+    bounce_phase<kSmem, false>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
 }
 
 /* ======================================================================== */
@@ -970,7 +1097,7 @@ __device__ __forceinline__ HitInfo intersect_scene_dev(const SceneViewT<kSmem>& 
 {
     HitInfo h;
     uint32_t tri;
-    trace_nearest<kSmem, false>(sc, o, d, h.t, tri);
+    trace_nearest<kSmem, false, false>(sc, o, d, h.t, tri);
     h.hit = tri != 0xFFFFFFFFu;
     h.pos = rv_make(0.0f, 0.0f, 0.0f);
     h.normal = rv_make(0.0f, 0.0f, 0.0f);
@@ -1326,41 +1453,46 @@ namespace rvpt
 
 static size_t smem_bytes_for(const FrameParams& p, bool smem) { return smem ? p.layout.bytes : 0; }
 
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 cudaError_t configure_kernels(size_t max_dynamic_smem)
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_frame<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_dynamic_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_frame<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_dynamic_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_dynamic_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_dynamic_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_modes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_dynamic_smem);
-    return e;
+    if ((e = set_smem(k_frame<true, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_primary<true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_bounce<true>, max_dynamic_smem)) != cudaSuccess) return e;
+    return set_smem(k_modes<true>, max_dynamic_smem);
 }
 
-size_t frame_smem_bytes(size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris)
+size_t frame_smem_bytes(size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris, bool oct)
 {
-    /* blob + origin-relative node copy + one float per triangle */
-    return scene_bytes + (size_t)n_nodes * 32u + (((size_t)n_tris * 4u + 15u) & ~(size_t)15u);
+    /* blob + one float per triangle + the derived node copies: 8 absolute + 8
+     * origin-relative octant copies, or one origin-relative copy */
+    const size_t rel_num = ((size_t)n_tris * 4u + 15u) & ~(size_t)15u;
+    return scene_bytes + rel_num + (size_t)n_nodes * 32u * (oct ? 16u : 1u);
 }
 
 cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bounce_ctas_per_sm,
-                      bool smem, size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris)
+                      bool smem, bool oct, size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris)
 {
     const size_t dyn = smem ? scene_bytes : 0;
     cudaError_t e;
     if (smem)
     {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<true, true>,
-                                                          kThreads, frame_smem_bytes(scene_bytes, n_nodes, n_tris));
+        const size_t fdyn = frame_smem_bytes(scene_bytes, n_nodes, n_tris, oct);
+        if (oct)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
+                                                              k_frame<true, true, true>, kThreads, fdyn);
+        else
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
+                                                              k_frame<true, true, false>, kThreads, fdyn);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<true>,
                                                           kThreads, dyn);
@@ -1370,8 +1502,8 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
     }
     else
     {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm, k_frame<false, false>,
-                                                          kThreads, dyn);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
+                                                          k_frame<false, false, false>, kThreads, dyn);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<false>,
                                                           kThreads, dyn);
@@ -1382,21 +1514,24 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
     return e;
 }
 
-cudaError_t launch_frame(const FrameParams& p, bool smem, int grid, cudaStream_t st)
+cudaError_t launch_frame(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st)
 {
     void* args[] = {const_cast<FrameParams*>(&p)};
+    const void* k;
+    size_t dyn = 0;
     if (smem)
     {
-        const size_t dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris);
+        dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris, oct);
         /* the ortho camera has a different origin per ray: no shared-origin copies */
-        if (p.camera_mode != 1)
-            return cudaLaunchCooperativeKernel((const void*)k_frame<true, true>, dim3(grid),
-                                               dim3(kThreads), args, dyn, st);
-        return cudaLaunchCooperativeKernel((const void*)k_frame<true, false>, dim3(grid),
-                                           dim3(kThreads), args, dyn, st);
+        const bool rel = p.camera_mode != 1;
+        if (oct)
+            k = rel ? (const void*)k_frame<true, true, true> : (const void*)k_frame<true, false, true>;
+        else
+            k = rel ? (const void*)k_frame<true, true, false> : (const void*)k_frame<true, false, false>;
     }
-    return cudaLaunchCooperativeKernel((const void*)k_frame<false, false>, dim3(grid),
-                                       dim3(kThreads), args, 0, st);
+    else
+        k = (const void*)k_frame<false, false, false>;
+    return cudaLaunchCooperativeKernel(k, dim3(grid), dim3(kThreads), args, dyn, st);
 }
 
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)

@@ -8,6 +8,7 @@ kernels. Nothing here computes pixels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -58,6 +59,8 @@ class Engine:
                  rank: int = 0, nranks: int = 1):
         self._lib = _lib.load()
         self.width, self.height = int(width), int(height)
+        # RVPT_B200_EXTRA_FLAGS: developer knob to A/B kernel variants under bench.py / tools
+        flags |= int(os.environ.get("RVPT_B200_EXTRA_FLAGS", "0"), 0)
         self.flags = flags
         self._ctx = C.c_void_p()
         rc = self._lib.rvpt_b200_create(C.byref(self._ctx), device, width, height, flags)
@@ -178,6 +181,22 @@ class Engine:
         self._check(self._lib.rvpt_b200_get_kernel_times(self._ctx, C.byref(kt)))
         return {"primary_ms": kt.primary_ms, "bounce_ms": kt.bounce_ms,
                 "primary_launches": kt.primary_launches, "bounce_launches": kt.bounce_launches}
+
+    def set_timeline(self, enabled: bool) -> None:
+        """Per-CTA phase stamps of the frame kernel (after upload_scene)."""
+        self._check(self._lib.rvpt_b200_set_timeline(self._ctx, int(enabled)))
+
+    def timeline(self) -> np.ndarray:
+        """uint64 [n_ctas, n_slots] %globaltimer stamps (ns) of the last frame kernel, 0 =
+        phase not reached; slot meaning in include/rvpt_abi.h."""
+        n_ctas, n_slots = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.rvpt_b200_get_timeline(self._ctx, None, 0, C.byref(n_ctas),
+                                                     C.byref(n_slots)))
+        out = np.zeros((n_ctas.value, n_slots.value), np.uint64)
+        if out.size:
+            self._check(self._lib.rvpt_b200_get_timeline(self._ctx, out.ctypes.data, out.size,
+                                                         C.byref(n_ctas), C.byref(n_slots)))
+        return out
 
     # -- multi-GPU tiles --------------------------------------------------
     def tile_info(self) -> _lib.TileInfo:

@@ -468,3 +468,40 @@ def test_more_ranks_than_tiles(rv, builtin):
         acc += a
         eng.close()
     _assert_bit_equal(acc, full.read_accum_f32(), "4 ranks, 2 tiles")
+
+
+@pytest.mark.parametrize("scene_name", ["builtin", "cornell"])
+def test_octant_sorted_nodes_equal_minmax_walk(rv, oracle_mod, builtin, cornell, scene_name):
+    """The per-octant (near, far) node copies are an instruction-count optimisation of
+    intersect_aabb (intersection.glsl:327-357): same image with and without them, and both
+    equal to the oracle. The cornell pose looks straight down +z at axis-aligned walls
+    (zero-thickness boxes); the ortho camera's direction has exact zeros (slow path)."""
+    from rvpt_b200 import _lib
+    prep = builtin if scene_name == "builtin" else cornell
+    pose = PINNED_POSE if scene_name == "builtin" else CORNELL_POSE
+    for cam_mode in (0, 1):
+        a, ora, st_a = _render_both(rv, oracle_mod, prep, 208, 160, pose, frames=3, fov=60.0,
+                                    camera_mode=cam_mode)
+        b, _, st_b = _render_both(rv, oracle_mod, prep, 208, 160, pose, frames=3, fov=60.0,
+                                  flags=_lib.FLAG_NO_OCTANTS, oracle_flags=0, camera_mode=cam_mode)
+        _assert_bit_equal(a.read_accum_f32(), ora.accum, "octant copies vs oracle")
+        _assert_bit_equal(b.read_accum_f32(), ora.accum, "min/max walk vs oracle")
+        assert st_a[-1][0]["active"] == st_b[-1][0]["active"] == st_a[-1][1]
+
+
+def test_frame_kernel_timeline(rv, builtin):
+    """set_timeline: per-CTA phase stamps are monotone and cover the frame."""
+    W, H = 640, 360
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    eng.set_timeline(True)
+    eng.render_frame(rv.default_settings(frame=0), cam)
+    tl = eng.timeline()
+    assert tl.shape[0] >= 1 and tl.shape[1] == 16
+    assert (tl[:, 0] > 0).all() and (tl[:, 1] >= tl[:, 0]).all() and (tl[:, 2] >= tl[:, 1]).all()
+    span_us = (tl.max() - tl[:, 0].min()) / 1e3
+    assert 0 < span_us < 1e5
+    eng.set_timeline(False)
+    eng.render_frame(rv.default_settings(frame=1), cam)
+    assert eng.timeline().size == 0
