@@ -139,6 +139,10 @@ typedef struct rvpt_b200_stats
  * test then uses the reference's per-axis min/max form for every ray). Same
  * results; for A/B measurements. */
 #define RVPT_B200_FLAG_NO_OCTANTS 0x10u
+/* Render the frame with the barrier-free kernel (k_flow): every SM streams its
+ * own wavefront queue instead of the whole grid synchronising between bounce
+ * waves. Same results. */
+#define RVPT_B200_FLAG_FLOW 0x20u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 

@@ -13,6 +13,7 @@
 #define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
+#define RVPT_FLOW_RING 4096u        /* k_flow: path records in one CTA's ring queue */
 #define RVPT_TIMELINE_SLOTS 16u     /* per-CTA phase stamps of the last frame kernel */
 
 /*

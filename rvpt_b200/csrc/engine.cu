@@ -45,7 +45,7 @@ struct rvpt_b200_ctx
     int num_sms = 0;
     int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
     int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
-    int grid_frame = 0, grid_primary = 0, grid_bounce = 0;
+    int grid_frame = 0, grid_primary = 0, grid_bounce = 0, grid_flow = 0;
     uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
     uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
 
@@ -171,10 +171,13 @@ int ensure_frame_buffers(rvpt_b200_ctx* ctx)
     }
     for (int i = 0; i < 2; ++i)
     {
-        CU(cudaMalloc(&ctx->queue[i].q0, slots * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q1, slots * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q2, slots * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q3, slots * sizeof(float4)));
+        /* queue 0 doubles as the per-CTA rings of k_flow (at most 2 CTAs of 1024 threads per SM) */
+        const size_t entries =
+            i == 0 ? std::max(slots, (size_t)ctx->num_sms * 2u * RVPT_FLOW_RING) : slots;
+        CU(cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q3, entries * sizeof(float4)));
     }
     CU(cudaMalloc(&ctx->d_ctr, sizeof(FrameCounters)));
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(FrameCounters), ctx->stream));
@@ -487,9 +490,12 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
         if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
         CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, ctx->scene_oct, L.bytes, L.n_nodes,
                            L.n_tris));
-        if (occ_f < 1 || occ_p < 1 || occ_b < 1)
-            return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)",
-                        occ_f, occ_p, occ_b);
+        int occ_w = 0;
+        CU(rvpt::flow_occupancy(&occ_w, ctx->scene_smem, ctx->scene_oct, L.bytes, L.n_nodes, L.n_tris));
+        if (occ_f < 1 || occ_p < 1 || occ_b < 1 || occ_w < 1)
+            return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d/%d)",
+                        occ_f, occ_p, occ_b, occ_w);
+        ctx->grid_flow = ctx->num_sms * std::min(occ_w, 2);
         /* persistent grids: every CTA is resident (a requirement of the cooperative launch) */
         ctx->grid_frame = ctx->num_sms * occ_f;
         ctx->grid_primary = ctx->num_sms * occ_p;
@@ -530,7 +536,8 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (width == 0 || height == 0 || width > 65536 || height > 65536)
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
-                  RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS))
+                  RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
+                  RVPT_B200_FLAG_FLOW))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     ctx->device = device;
     ctx->W = width;
@@ -719,7 +726,13 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     {
         p.pass = pass;
         p.wave_set = ctx->launch_seq & 1u;
-        if (!unfused)
+        if (ctx->flags & RVPT_B200_FLAG_FLOW)
+        {
+            ScopedTimer tm(ctx, 0);
+            CU(rvpt::launch_flow(p, ctx->scene_smem, ctx->scene_oct, ctx->grid_flow, ctx->stream));
+            ++launches;
+        }
+        else if (!unfused)
         {
             ScopedTimer tm(ctx, 0);
             CU(rvpt::launch_frame(p, ctx->scene_smem, ctx->scene_oct, ctx->grid_frame, ctx->stream));
@@ -930,10 +943,11 @@ extern "C" int rvpt_b200_set_timeline(rvpt_b200_ctx* ctx, int enabled)
     ctx->timeline_ctas = 0;
     if (enabled)
     {
-        const size_t bytes = (size_t)ctx->grid_frame * RVPT_TIMELINE_SLOTS * sizeof(unsigned long long);
+        const int ctas = std::max(ctx->grid_frame, ctx->grid_flow);
+        const size_t bytes = (size_t)ctas * RVPT_TIMELINE_SLOTS * sizeof(unsigned long long);
         CU(cudaMalloc(&ctx->d_timeline, bytes));
         CU(cudaMemset(ctx->d_timeline, 0, bytes));
-        ctx->timeline_ctas = ctx->grid_frame;
+        ctx->timeline_ctas = ctas;
     }
     return 0;
 }

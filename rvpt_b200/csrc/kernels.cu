@@ -971,6 +971,337 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
 }
 
 /* ======================================================================== */
+/* k_flow: the whole frame as ONE barrier-free stream of work per SM          */
+/* ======================================================================== */
+/*
+ * k_frame separates the bounce waves with grid barriers; the timeline
+ * (profiles/) shows 13-16 % of a frame waiting at them. Here every CTA keeps
+ * its own wavefront queue — a ring of RVPT_FLOW_RING 64-byte SoA path records
+ * in HBM (L2-resident), produced and consumed by the warps of that CTA only,
+ * so all synchronisation is shared-memory atomics inside the CTA and there is
+ * no grid-wide barrier at all:
+ *
+ *   warp loop:  a full 32-ray group is committed in my CTA's ring -> pop it, trace one
+ *               bounce, terminated lanes accumulate, survivors are appended
+ *               (depth + 1);
+ *               else claim a 32-pixel primary chunk (global sharded counter, as in
+ *               k_frame), generate + trace bounce 0, append survivors (depth 1);
+ *               else (no primary work left anywhere, nobody in my CTA can still
+ *               append) pop the final partial group and run it to the end in-thread;
+ *               ring empty -> exit.
+ *
+ * Popping has priority, so a ring holds little more than one group per warp; primary
+ * claims stop while the backlog exceeds RVPT_FLOW_LIMIT, which bounds it strictly
+ * (LIMIT + 32 warps x 32 appends in flight < RING). Entry (ring index) i lives in group
+ * i / 32; gstate[group % GROUPS] = generation << 8 | committed entries: appenders wait
+ * for their group's generation (the previous occupant was consumed — never the case in
+ * practice), write, fence, add their count; the consumer of a group bumps the generation
+ * after its loads. Results do not depend on any of this: a path carries its pixel slot,
+ * RNG state and depth, and each pixel is accumulated exactly once per pass.
+ */
+#define RVPT_FLOW_GROUPS (RVPT_FLOW_RING / 32u)
+#define RVPT_FLOW_LIMIT (RVPT_FLOW_RING / 2u)
+
+struct FlowShared
+{
+    uint32_t lock;      /* guards the pop decision (rd, tail handling) */
+    uint32_t res;       /* entries reserved so far (monotonic) */
+    uint32_t rd;        /* groups popped so far (monotonic) */
+    uint32_t active;    /* work units in flight that may still append */
+    uint32_t prim_done; /* a warp of this CTA found the primary counters exhausted */
+    uint32_t pad[3];
+    uint32_t gstate[RVPT_FLOW_GROUPS];
+    uint32_t hist[RVPT_MAX_BOUNCE_STATS]; /* rays traced at depth k >= 1 by this CTA */
+};
+
+enum : uint32_t { FLOW_POP = 1, FLOW_POP_TAIL = 2, FLOW_PRIMARY = 3, FLOW_WAIT = 4, FLOW_EXIT = 5 };
+
+/* acquire/release fence at CTA scope (the MEMBAR.SC of __threadfence_block is not needed) */
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* a)
+{
+    return *reinterpret_cast<const volatile uint32_t*>(a);
+}
+
+/* Append the surviving lanes (depth = index of the bounce they trace next). */
+__device__ __forceinline__ void flow_push(const FrameParams& p, FlowShared& fs, bool alive, uint32_t slot,
+                                          const PathState& s, uint32_t depth)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
+    if (mask == 0) return;
+    const uint32_t cnt = (uint32_t)__popc(mask);
+    uint32_t base = 0;
+    if (lane == 0)
+    {
+        base = atomicAdd(&fs.res, cnt);
+        /* ring slots of both groups touched must have been consumed one lap ago */
+        const uint32_t g0 = base >> 5, g1 = (base + cnt - 1u) >> 5;
+        uint32_t spins = 0;
+        while ((ld_volatile_shared(&fs.gstate[g0 % RVPT_FLOW_GROUPS]) >> 8) != ((g0 / RVPT_FLOW_GROUPS) & 0xFFFFFFu) ||
+               (ld_volatile_shared(&fs.gstate[g1 % RVPT_FLOW_GROUPS]) >> 8) != ((g1 / RVPT_FLOW_GROUPS) & 0xFFFFFFu))
+        {
+            if (++spins > (1u << 22)) __trap(); /* never hang the GPU */
+            __nanosleep(32);
+        }
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (alive)
+    {
+        const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        const uint32_t i = blockIdx.x * RVPT_FLOW_RING + (e % RVPT_FLOW_RING);
+        const PathQueue& q = p.queue[0];
+        __stcs(&q.q0[i], make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot)));
+        __stcs(&q.q1[i], make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.rng)));
+        __stcs(&q.q2[i], make_float4(s.thr.x, s.thr.y, s.thr.z, __uint_as_float(depth)));
+        __stcs(&q.q3[i], make_float4(s.col.x, s.col.y, s.col.z, 0.0f));
+        fence_cta(); /* the records before the commit, for the warps of this CTA */
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        const uint32_t g0 = base >> 5;
+        const uint32_t n0 = min(cnt, (g0 + 1u) * 32u - base);
+        atomicAdd(&fs.gstate[g0 % RVPT_FLOW_GROUPS], n0);
+        if (cnt > n0) atomicAdd(&fs.gstate[(g0 + 1u) % RVPT_FLOW_GROUPS], cnt - n0);
+    }
+}
+
+__device__ __forceinline__ void flow_retire(FlowShared& fs)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0)
+    {
+        fence_cta();
+        atomicSub(&fs.active, 1u);
+    }
+}
+
+/* Claim one primary chunk from the sharded global counters (see primary_phase). */
+__device__ __forceinline__ uint32_t flow_claim_chunk(const FrameParams& p, WaveCounters& wc, uint32_t& shard)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_units = p.n_chunks;
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
+    uint32_t unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+    while (unit >= n_units)
+    {
+        uint32_t v = 0xFFFFFFFFu;
+        if (lane < RVPT_CHUNK_SHARDS) v = *reinterpret_cast<volatile uint32_t*>(&wc.chunk_ctr[lane * 32u]);
+        const bool has_work = lane < RVPT_CHUNK_SHARDS && (uint64_t)v * RVPT_CHUNK_SHARDS + lane < n_units;
+        const uint32_t live = __ballot_sync(0xFFFFFFFFu, has_work);
+        if (live == 0) return 0xFFFFFFFFu;
+        const uint32_t rot = (live >> (shard + 1u)) | (live << (RVPT_CHUNK_SHARDS - 1u - shard));
+        shard = (shard + 1u + (uint32_t)(__ffs(rot & 0xFFFFu) - 1)) % RVPT_CHUNK_SHARDS;
+        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
+        unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+    }
+    return unit;
+}
+
+template <bool kSmem, bool kRel, bool kOct>
+__device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT<kSmem>& sc, FlowShared& fs)
+{
+    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    const uint32_t lane = threadIdx.x & 31u;
+    const PathQueue& q = p.queue[0];
+    uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
+    uint32_t traced = 0; /* primary rays of this warp: < 2^32 per launch */
+    uint32_t idle_spins = 0;
+
+    for (;;)
+    {
+        uint32_t kind = 0, g = 0, n = 0;
+        if (lane == 0)
+        {
+            uint32_t spins = 0;
+            while (atomicCAS(&fs.lock, 0u, 1u) != 0u)
+                if (++spins > (1u << 24)) __trap();
+            fence_cta();
+            g = ld_volatile_shared(&fs.rd);
+            const uint32_t st = ld_volatile_shared(&fs.gstate[g % RVPT_FLOW_GROUPS]);
+            const uint32_t backlog = ld_volatile_shared(&fs.res) - g * 32u;
+            if (st == ((((g / RVPT_FLOW_GROUPS) & 0xFFFFFFu) << 8) | 32u))
+            {
+                fs.rd = g + 1u;
+                atomicAdd(&fs.active, 1u);
+                kind = FLOW_POP;
+                n = 32u;
+            }
+            else if (ld_volatile_shared(&fs.prim_done))
+            {
+                if (ld_volatile_shared(&fs.active) != 0u)
+                    kind = FLOW_WAIT; /* somebody may still append */
+                else
+                {
+                    /* nothing in flight: every reserved entry is committed and res is final */
+                    n = ld_volatile_shared(&fs.res) - g * 32u;
+                    if (n == 0u)
+                        kind = FLOW_EXIT;
+                    else if (n >= 32u)
+                        kind = FLOW_WAIT; /* the group filled up while we looked: next round pops it */
+                    else
+                    {
+                        fs.rd = g + 1u;
+                        fs.res = (g + 1u) * 32u; /* the rest of this group stays unused */
+                        atomicAdd(&fs.active, 1u);
+                        kind = FLOW_POP_TAIL;
+                    }
+                }
+            }
+            else if (backlog >= RVPT_FLOW_LIMIT)
+                kind = FLOW_WAIT;
+            else
+            {
+                atomicAdd(&fs.active, 1u);
+                kind = FLOW_PRIMARY;
+            }
+            fence_cta();
+            atomicExch(&fs.lock, 0u);
+        }
+        kind = __shfl_sync(0xFFFFFFFFu, kind, 0);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        if (kind == FLOW_EXIT) break;
+        if (kind == FLOW_WAIT)
+        {
+            if (++idle_spins > (1u << 22)) __trap();
+            __nanosleep(100);
+            continue;
+        }
+        idle_spins = 0;
+
+        if (kind == FLOW_PRIMARY)
+        {
+            const uint32_t c = flow_claim_chunk(p, wc, shard);
+            if (c == 0xFFFFFFFFu)
+            {
+                if (lane == 0) atomicExch(&fs.prim_done, 1u);
+                flow_retire(fs);
+                continue;
+            }
+            const uint32_t slot = c * 32u + lane;
+            uint32_t x, y;
+            slot_to_xy(p, slot, x, y);
+            const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
+                                ((slot >> 8) * p.nranks + p.rank < p.n_tiles) &&
+                                (p.all_kajiya || integrator_of(p, x, y) == 9);
+            bool alive = false;
+            PathState s;
+            if (inside)
+            {
+                prefetch_prev(p, slot);
+                if (p.pass == 0)
+                    s.rng = rv_wang_hash(x + y * p.W) + p.frame;
+                else
+                    s.rng = __float_as_uint(p.carry[slot].w);
+                const float jx = rv_rand(&s.rng);
+                const float jy = rv_rand(&s.rng);
+                const float cx = ((float)x + jx) * p.inv_dim_x;
+                float cy = ((float)y + jy) * p.inv_dim_y;
+                cy = 1.0f - cy;
+                camera_ray(p, cx, cy, s.o, s.d);
+                s.thr = rv_make(1.0f, 1.0f, 1.0f);
+                s.col = rv_make(0.0f, 0.0f, 0.0f);
+                rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
+                if (p.max_bounces > 0)
+                {
+                    alive = kajiya_step<kSmem, kRel, kOct>(sc, s, sample);
+                    if (alive && p.max_bounces == 1)
+                    {
+                        alive = false; /* integrators.glsl:674-675 */
+                        sample = rv_make(0.0f, 0.0f, 0.0f);
+                    }
+                }
+                if (!alive) finish_sample(p, slot, sample, s.rng, y * p.W + x);
+            }
+            if (p.max_bounces > 0)
+                traced += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, inside));
+            flow_push(p, fs, alive, slot, s, 1u);
+            flow_retire(fs);
+            continue;
+        }
+
+        /* FLOW_POP / FLOW_POP_TAIL: group g, n entries */
+        {
+            const bool mine = lane < n;
+            bool alive = false;
+            PathState s;
+            uint32_t slot = 0, depth = 0;
+            if (mine)
+            {
+                const uint32_t i = blockIdx.x * RVPT_FLOW_RING + ((g * 32u + lane) % RVPT_FLOW_RING);
+                const float4 a0 = __ldcg(&q.q0[i]);
+                const float4 a1 = __ldcg(&q.q1[i]);
+                const float4 a2 = __ldcg(&q.q2[i]);
+                const float4 a3 = __ldcg(&q.q3[i]);
+                s.o = rv_make(a0.x, a0.y, a0.z);
+                slot = __float_as_uint(a0.w);
+                s.d = rv_make(a1.x, a1.y, a1.z);
+                s.rng = __float_as_uint(a1.w);
+                s.thr = rv_make(a2.x, a2.y, a2.z);
+                depth = __float_as_uint(a2.w);
+                s.col = rv_make(a3.x, a3.y, a3.z);
+                prefetch_prev(p, slot);
+                fence_cta(); /* loads before the ring slots are handed back */
+            }
+            __syncwarp();
+            if (lane == 0)
+                atomicExch(&fs.gstate[g % RVPT_FLOW_GROUPS], (((g / RVPT_FLOW_GROUPS) + 1u) & 0xFFFFFFu) << 8);
+            if (mine)
+            {
+                /* rays traced per depth: one shared-memory atomic per distinct depth in the group */
+                const uint32_t peers = __match_any_sync(n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u), depth);
+                if (lane == (uint32_t)(__ffs(peers) - 1) && depth < RVPT_MAX_BOUNCE_STATS)
+                    atomicAdd(&fs.hist[depth], (uint32_t)__popc(peers));
+                rv_f3 sample;
+                for (uint32_t k = depth;; ++k)
+                {
+                    if (k != depth && k < RVPT_MAX_BOUNCE_STATS) atomicAdd(&fs.hist[k], 1u);
+                    alive = kajiya_step<kSmem, false, kOct>(sc, s, sample);
+                    if (alive && (int)k == p.max_bounces - 1)
+                    {
+                        alive = false; /* integrators.glsl:674-675: col is discarded */
+                        sample = rv_make(0.0f, 0.0f, 0.0f);
+                    }
+                    if (kind != FLOW_POP_TAIL || !alive) break;
+                }
+                if (!alive) finish_sample(p, slot, sample, s.rng);
+            }
+            if (kind == FLOW_POP) flow_push(p, fs, alive, slot, s, depth + 1u);
+            flow_retire(fs);
+        }
+    }
+    if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], (unsigned long long)traced);
+}
+
+template <bool kSmem, bool kRel, bool kOct>
+__global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_flow(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ FlowShared fs;
+
+    stamp(p, 0);
+    for (uint32_t i = threadIdx.x; i < sizeof(FlowShared) / 4u; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&fs)[i] = 0u;
+    clear_next_counters(p);
+    __syncthreads();
+    const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);
+    stamp(p, 1);
+
+    flow_loop<kSmem, kRel, kOct>(p, sc, fs);
+    stamp(p, 2);
+
+    __syncthreads();
+    if (threadIdx.x < RVPT_MAX_BOUNCE_STATS && threadIdx.x >= 1u && fs.hist[threadIdx.x])
+        atomicAdd(&p.ctr->stats[p.stats_set].active[threadIdx.x], (unsigned long long)fs.hist[threadIdx.x]);
+    stamp(p, 3);
+}
+
+/* ======================================================================== */
 /* unfused variant: one launch per wave (profiling / cross-check)             */
 /* ======================================================================== */
 template <bool kSmem>
@@ -1466,6 +1797,10 @@ cudaError_t configure_kernels(size_t max_dynamic_smem)
     if ((e = set_smem(k_frame<true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_frame<true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_frame<true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_flow<true, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_flow<true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_flow<true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_flow<true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_primary<true>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_bounce<true>, max_dynamic_smem)) != cudaSuccess) return e;
     return set_smem(k_modes<true>, max_dynamic_smem);
@@ -1532,6 +1867,41 @@ cudaError_t launch_frame(const FrameParams& p, bool smem, bool oct, int grid, cu
     else
         k = (const void*)k_frame<false, false, false>;
     return cudaLaunchCooperativeKernel(k, dim3(grid), dim3(kThreads), args, dyn, st);
+}
+
+/* k_flow needs no co-residency (no CTA ever waits for another CTA): plain launch */
+cudaError_t launch_flow(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st)
+{
+    if (smem)
+    {
+        const size_t dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris, oct);
+        const bool rel = p.camera_mode != 1;
+        if (oct && rel)
+            k_flow<true, true, true><<<grid, kThreads, dyn, st>>>(p);
+        else if (oct)
+            k_flow<true, false, true><<<grid, kThreads, dyn, st>>>(p);
+        else if (rel)
+            k_flow<true, true, false><<<grid, kThreads, dyn, st>>>(p);
+        else
+            k_flow<true, false, false><<<grid, kThreads, dyn, st>>>(p);
+    }
+    else
+        k_flow<false, false, false><<<grid, kThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t flow_occupancy(int* ctas_per_sm, bool smem, bool oct, size_t scene_bytes, uint32_t n_nodes,
+                           uint32_t n_tris)
+{
+    if (!smem)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<false, false, false>,
+                                                             kThreads, 0);
+    const size_t dyn = frame_smem_bytes(scene_bytes, n_nodes, n_tris, oct);
+    if (oct)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<true, true, true>,
+                                                             kThreads, dyn);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<true, true, false>, kThreads,
+                                                         dyn);
 }
 
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)

@@ -505,3 +505,66 @@ def test_frame_kernel_timeline(rv, builtin):
     eng.set_timeline(False)
     eng.render_frame(rv.default_settings(frame=1), cam)
     assert eng.timeline().size == 0
+
+
+# ---- k_flow: the barrier-free frame kernel (RVPT_B200_FLAG_FLOW) ----------------------------
+
+@pytest.mark.parametrize("case", ["builtin_default", "builtin_pinned", "cornell", "cornell_aa2",
+                                  "cornell_b1", "cornell_b2", "cornell_b16", "ortho", "rgba8",
+                                  "no_octants", "global_path"])
+def test_flow_kernel_bit_exact(rv, oracle_mod, builtin, cornell, case):
+    """Every SM streaming its own wavefront queue (no grid barriers) is the same computation:
+    bit-exact against the oracle, same per-bounce ray counts."""
+    from rvpt_b200 import _lib
+    F = _lib.FLAG_FLOW
+    kw = dict(frames=2)
+    prep, W, H, pose, flags = cornell, 176, 128, CORNELL_POSE, F
+    if case.startswith("builtin"):
+        prep, W, H = builtin, 256, 256
+        pose = DEFAULT_POSE if case == "builtin_default" else PINNED_POSE
+    elif case == "cornell":
+        kw.update(frames=3, fov=60.0)
+    elif case == "cornell_aa2":
+        kw.update(fov=60.0, aa=2)
+    elif case.startswith("cornell_b"):
+        kw.update(fov=60.0, max_bounces=int(case[9:]))
+    elif case == "ortho":
+        prep, pose = builtin, PINNED_POSE
+        kw.update(camera_mode=1)
+    elif case == "rgba8":
+        prep, pose, flags = builtin, DEFAULT_POSE, F | _lib.FLAG_ACCUM_RGBA8
+    elif case == "no_octants":
+        kw.update(fov=60.0)
+        flags = F | _lib.FLAG_NO_OCTANTS
+    if case == "global_path":
+        from conftest import PreparedScene
+        prep = PreparedScene(rv, rv.displaced_sphere_scene(20000))
+        W, H, pose = 160, 96, (0.0, 1.2, -3.0)
+        kw.update(frames=2, fov=60.0)
+    oflags = flags & _lib.FLAG_ACCUM_RGBA8
+    eng, ora, stats = _render_both(rv, oracle_mod, prep, W, H, pose, flags=flags, oracle_flags=oflags, **kw)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"flow kernel, {case}")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    st, active = stats[-1]
+    assert st["active"] == active
+    assert st["kernel_launches"] == kw.get("aa", 1)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (17, 33), (640, 360)])
+def test_flow_kernel_sizes_and_partition(rv, oracle_mod, builtin, size):
+    """Ragged / tiny images (most CTAs never get a chunk) and a 3-way tile partition."""
+    from rvpt_b200 import _lib
+    W, H = size
+    eng, ora, _ = _render_both(rv, oracle_mod, builtin, W, H, DEFAULT_POSE, frames=2, flags=_lib.FLAG_FLOW,
+                               oracle_flags=0)
+    full = eng.read_accum_f32()
+    _assert_bit_equal(full, ora.accum, f"flow kernel {W}x{H}")
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    acc = np.zeros_like(full)
+    for r in range(3):
+        part = rv.Engine(W, H, flags=_lib.FLAG_FLOW, rank=r, nranks=3)
+        part.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+        for f in range(2):
+            part.render_frame(rv.default_settings(frame=f), cam)
+        acc += part.read_accum_f32()
+    _assert_bit_equal(acc, full, "flow kernel, 3-way partition")
