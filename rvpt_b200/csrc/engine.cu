@@ -537,7 +537,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
-                  RVPT_B200_FLAG_FLOW))
+                  RVPT_B200_FLAG_FLOW | 0x40000000u /* reserved: A/B experiments */))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     ctx->device = device;
     ctx->W = width;

@@ -1008,13 +1008,12 @@ struct FlowShared
     uint32_t res;       /* entries reserved so far (monotonic) */
     uint32_t rd;        /* groups popped so far (monotonic) */
     uint32_t active;    /* work units in flight that may still append */
-    uint32_t prim_done; /* a warp of this CTA found the primary counters exhausted */
-    uint32_t pad[3];
+    uint32_t pad[4];
     uint32_t gstate[RVPT_FLOW_GROUPS];
     uint32_t hist[RVPT_MAX_BOUNCE_STATS]; /* rays traced at depth k >= 1 by this CTA */
 };
 
-enum : uint32_t { FLOW_POP = 1, FLOW_POP_TAIL = 2, FLOW_PRIMARY = 3, FLOW_WAIT = 4, FLOW_EXIT = 5 };
+enum : uint32_t { FLOW_POP = 1, FLOW_POP_TAIL = 2, FLOW_PRIMARY = 3, FLOW_WAIT = 4, FLOW_EXIT = 5, FLOW_RETRY = 6 };
 
 /* acquire/release fence at CTA scope (the MEMBAR.SC of __threadfence_block is not needed) */
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
@@ -1071,20 +1070,17 @@ __device__ __forceinline__ void flow_push(const FrameParams& p, FlowShared& fs, 
 __device__ __forceinline__ void flow_retire(FlowShared& fs)
 {
     __syncwarp();
-    if ((threadIdx.x & 31u) == 0)
-    {
-        fence_cta();
-        atomicSub(&fs.active, 1u);
-    }
+    if ((threadIdx.x & 31u) == 0) atomicSub(&fs.active, 1u); /* after this warp's commits, in program order */
 }
 
-/* Claim one primary chunk from the sharded global counters (see primary_phase). */
-__device__ __forceinline__ uint32_t flow_claim_chunk(const FrameParams& p, WaveCounters& wc, uint32_t& shard)
+/* Resolve a claim issued earlier on `shard` of the sharded global chunk counters into a chunk
+ * index; a dry shard is left for the next one that still has work (see primary_phase).
+ * 0xFFFFFFFF: no primary chunk is left anywhere. */
+__device__ __forceinline__ uint32_t flow_resolve_claim(const FrameParams& p, WaveCounters& wc, uint32_t& shard,
+                                                       uint32_t claim)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_units = p.n_chunks;
-    uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
     uint32_t unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
     while (unit >= n_units)
     {
@@ -1110,77 +1106,99 @@ __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT
     uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
     uint32_t traced = 0; /* primary rays of this warp: < 2^32 per launch */
     uint32_t idle_spins = 0;
+    /* The claim for the next primary chunk is always in flight (issued before the current
+     * unit is processed), so its round trip to the L2 atomic unit is off the critical path.
+     * A warp holding a claim is counted in `active`: it may still append. */
+    bool holding = true; /* the first claim of every warp is counted in fs.active by k_flow's set-up */
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
 
     for (;;)
     {
         uint32_t kind = 0, g = 0, n = 0;
         if (lane == 0)
         {
-            uint32_t spins = 0;
-            while (atomicCAS(&fs.lock, 0u, 1u) != 0u)
-                if (++spins > (1u << 24)) __trap();
-            fence_cta();
+            /* Lock-free decision on shared-memory words (volatile + atomics; the shared
+             * pipeline executes one thread's accesses in order). A unit is counted in
+             * `active` BEFORE it is claimed, so active == 0 proves nothing can append. */
             g = ld_volatile_shared(&fs.rd);
             const uint32_t st = ld_volatile_shared(&fs.gstate[g % RVPT_FLOW_GROUPS]);
-            const uint32_t backlog = ld_volatile_shared(&fs.res) - g * 32u;
             if (st == ((((g / RVPT_FLOW_GROUPS) & 0xFFFFFFu) << 8) | 32u))
             {
-                fs.rd = g + 1u;
                 atomicAdd(&fs.active, 1u);
-                kind = FLOW_POP;
-                n = 32u;
-            }
-            else if (ld_volatile_shared(&fs.prim_done))
-            {
-                if (ld_volatile_shared(&fs.active) != 0u)
-                    kind = FLOW_WAIT; /* somebody may still append */
+                if (atomicCAS(&fs.rd, g, g + 1u) == g)
+                {
+                    kind = FLOW_POP;
+                    n = 32u;
+                }
                 else
                 {
-                    /* nothing in flight: every reserved entry is committed and res is final */
-                    n = ld_volatile_shared(&fs.res) - g * 32u;
-                    if (n == 0u)
-                        kind = FLOW_EXIT;
-                    else if (n >= 32u)
-                        kind = FLOW_WAIT; /* the group filled up while we looked: next round pops it */
-                    else
-                    {
-                        fs.rd = g + 1u;
-                        fs.res = (g + 1u) * 32u; /* the rest of this group stays unused */
-                        atomicAdd(&fs.active, 1u);
-                        kind = FLOW_POP_TAIL;
-                    }
+                    atomicSub(&fs.active, 1u); /* another warp took it: look again */
+                    kind = FLOW_RETRY;
                 }
             }
-            else if (backlog >= RVPT_FLOW_LIMIT)
-                kind = FLOW_WAIT;
-            else
+            else if (!holding)
             {
-                atomicAdd(&fs.active, 1u);
-                kind = FLOW_PRIMARY;
+                /* drain: the final partial group. Serialised by a lock; no pop can race with
+                 * it, because a pop needs a full head group and nobody can append any more. */
+                kind = FLOW_WAIT;
+                if (ld_volatile_shared(&fs.active) == 0u &&
+                    ld_volatile_shared(&fs.res) == ld_volatile_shared(&fs.rd) * 32u)
+                    kind = FLOW_EXIT; /* nobody can append any more and the ring is empty: final */
+                else if (ld_volatile_shared(&fs.active) == 0u && atomicCAS(&fs.lock, 0u, 1u) == 0u)
+                {
+                    g = ld_volatile_shared(&fs.rd);
+                    n = ld_volatile_shared(&fs.res) - g * 32u;
+                    if (ld_volatile_shared(&fs.active) != 0u || n >= 32u)
+                        kind = FLOW_RETRY; /* raced with the last commit: a full group is poppable */
+                    else if (n == 0u)
+                        kind = FLOW_EXIT;
+                    else
+                    {
+                        atomicAdd(&fs.active, 1u);
+                        *reinterpret_cast<volatile uint32_t*>(&fs.res) = (g + 1u) * 32u; /* rest of the group stays unused */
+                        *reinterpret_cast<volatile uint32_t*>(&fs.rd) = g + 1u;
+                        kind = FLOW_POP_TAIL;
+                    }
+                    atomicExch(&fs.lock, 0u);
+                }
             }
-            fence_cta();
-            atomicExch(&fs.lock, 0u);
+            else if (ld_volatile_shared(&fs.res) - g * 32u >= RVPT_FLOW_LIMIT)
+                kind = FLOW_WAIT; /* backlog bound: let the head group commit first */
+            else
+                kind = FLOW_PRIMARY; /* the held claim is already counted in `active` */
         }
         kind = __shfl_sync(0xFFFFFFFFu, kind, 0);
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
         n = __shfl_sync(0xFFFFFFFFu, n, 0);
         if (kind == FLOW_EXIT) break;
+        if (kind == FLOW_RETRY) continue;
+        /* acquire side of the commit counters: the records of a popped group were released
+         * by their writers' fence + shared-memory atomic */
+        if ((kind == FLOW_POP || kind == FLOW_POP_TAIL) && !(p.flags & 0x40000000u)) fence_cta();
         if (kind == FLOW_WAIT)
         {
-            if (++idle_spins > (1u << 22)) __trap();
-            __nanosleep(100);
+            /* Waiting warps must not take issue slots from the warps they wait for: sleep with
+             * exponential back-off, 0.25 .. 2 us (a polling warp costs ~45 instructions a round). */
+            if (++idle_spins > (1u << 20)) __trap(); /* ~2 s: never hang the GPU */
+            __nanosleep((256u << min(idle_spins - 1u, 3u)) + ((threadIdx.x >> 5) * 37u & 255u));
             continue;
         }
         idle_spins = 0;
 
         if (kind == FLOW_PRIMARY)
         {
-            const uint32_t c = flow_claim_chunk(p, wc, shard);
+            const uint32_t c = flow_resolve_claim(p, wc, shard, claim);
             if (c == 0xFFFFFFFFu)
             {
-                if (lane == 0) atomicExch(&fs.prim_done, 1u);
+                holding = false; /* this warp only pops from now on */
                 flow_retire(fs);
                 continue;
+            }
+            if (lane == 0)
+            {
+                atomicAdd(&fs.active, 1u);
+                claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
             }
             const uint32_t slot = c * 32u + lane;
             uint32_t x, y;
@@ -1229,7 +1247,7 @@ __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT
             const bool mine = lane < n;
             bool alive = false;
             PathState s;
-            uint32_t slot = 0, depth = 0;
+            uint32_t slot = 0, depth = 0, dep = 0;
             if (mine)
             {
                 const uint32_t i = blockIdx.x * RVPT_FLOW_RING + ((g * 32u + lane) % RVPT_FLOW_RING);
@@ -1245,11 +1263,19 @@ __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT
                 depth = __float_as_uint(a2.w);
                 s.col = rv_make(a3.x, a3.y, a3.z);
                 prefetch_prev(p, slot);
-                fence_cta(); /* loads before the ring slots are handed back */
+                /* the ring slots are handed back only after the four loads have returned: the
+                 * new generation value is made data-dependent on them (lane 0 is always `mine`,
+                 * and a warp-wide load retires as one instruction) */
+                asm volatile("{\n\t.reg .b32 t;\n\t"
+                             "or.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
+                             "and.b32 %0, t, 0;\n\t}"
+                             : "=r"(dep)
+                             : "r"(__float_as_uint(a0.w)), "r"(__float_as_uint(a1.w)),
+                               "r"(__float_as_uint(a2.w)), "r"(__float_as_uint(a3.w)));
             }
-            __syncwarp();
             if (lane == 0)
-                atomicExch(&fs.gstate[g % RVPT_FLOW_GROUPS], (((g / RVPT_FLOW_GROUPS) + 1u) & 0xFFFFFFu) << 8);
+                atomicExch(&fs.gstate[g % RVPT_FLOW_GROUPS],
+                           ((((g / RVPT_FLOW_GROUPS) + 1u) & 0xFFFFFFu) << 8) + dep);
             if (mine)
             {
                 /* rays traced per depth: one shared-memory atomic per distinct depth in the group */
@@ -1287,6 +1313,8 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_flow(const FramePar
     stamp(p, 0);
     for (uint32_t i = threadIdx.x; i < sizeof(FlowShared) / 4u; i += blockDim.x)
         reinterpret_cast<uint32_t*>(&fs)[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) fs.active = blockDim.x >> 5; /* every warp starts out holding one primary claim */
     clear_next_counters(p);
     __syncthreads();
     const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);

@@ -1,0 +1,29 @@
+#!/bin/bash
+# flow kernel iteration: flow tests, A/B bench (frame / flow / flow without consumer fence), timeline
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -k "flow" 2>&1 | tail -5
+for v in frame flow flownf; do
+  case $v in
+    frame) unset RVPT_B200_EXTRA_FLAGS;;
+    flow) export RVPT_B200_EXTRA_FLAGS=0x20;;
+    flownf) export RVPT_B200_EXTRA_FLAGS=0x40000020;;
+  esac
+  timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${v}_n1.json 2> gpurun_out/bench_${v}_n1.err
+  timeout 300 python bench.py --steps 30 --warmup 3 --pose pinned --no-cpu-baseline > gpurun_out/bench_${v}_pinned.json 2>/dev/null
+  timeout 300 python bench.py --steps 10 --warmup 3 --scene cornell --no-cpu-baseline > gpurun_out/bench_${v}_cornell.json 2>/dev/null
+done
+python - <<PY
+import json
+for v in ('frame','flow','flownf'):
+  for n in ('n1','pinned','cornell'):
+    try:
+        d=json.load(open('gpurun_out/bench_%s_%s.json'%(v,n)))
+        r=d['roofline']
+        print(v, n, 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms/frame', round(r['frame_ms_in_timed_region'],4), 'frac', round(r['frac'],3), r['active_per_bounce'][:4], d['clocks']['sm_mhz'])
+    except Exception as e:
+        print(v, n, 'failed', e)
+PY
+tail -3 gpurun_out/bench_flow_n1.err
+export RVPT_B200_EXTRA_FLAGS=0x20
+timeout 120 python tools/timeline.py > gpurun_out/timeline_flow_builtin.md 2>&1; tail -8 gpurun_out/timeline_flow_builtin.md
+timeout 120 python tools/timeline.py --scene cornell > gpurun_out/timeline_flow_cornell.md 2>&1; tail -6 gpurun_out/timeline_flow_cornell.md
