@@ -102,7 +102,9 @@ struct WaveCounters
     /* primary phase work distribution: one counter per shard, 128 B apart so the
      * shards live in different L2 atomic units; shard k hands out chunks k, k+16, ... */
     uint32_t chunk_ctr[RVPT_CHUNK_SHARDS * 32u];
-    uint32_t work_ctr[64]; /* bounce phase work distribution, per bounce */
+    uint32_t work_ctr[64]; /* bounce phase work distribution, per bounce (static + claimed eighth) */
+    /* k_frame's big bounce waves: sharded like chunk_ctr, wave b uses set b & 1 */
+    uint32_t bounce_ctr[2][RVPT_CHUNK_SHARDS * 32u];
     uint32_t qcount[64];   /* survivors pushed by bounce b (read by b+1) */
 };
 struct FrameStats
@@ -158,6 +160,7 @@ struct FrameParams
     uint32_t wave_set;            /* launch sequence parity */
     uint32_t stats_set;           /* frame sequence parity */
     uint32_t tail_threshold;      /* waves this small finish inside their threads */
+    uint32_t use_forecast;        /* wave-size forecast from the previous launch is meaningful */
     unsigned long long* timeline; /* optional [n_ctas][RVPT_TIMELINE_SLOTS] globaltimer stamps */
 };
 

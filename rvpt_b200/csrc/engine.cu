@@ -720,6 +720,8 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;
     /* a wave with at most two rays per resident warp runs to completion in its threads */
     p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * 2u;
+    /* the previous frame's per-bounce counts forecast this frame's small waves (k_frame) */
+    p.use_forecast = (!unfused && ctx->frame_seq > 0) ? 1u : 0u;
 
     uint32_t launches = 0;
     for (int pass = 0; pass < rs->aa && p.n_chunks > 0; ++pass)

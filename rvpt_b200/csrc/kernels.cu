@@ -635,16 +635,40 @@ __device__ __forceinline__ void camera_ray(const FrameParams& p, float cx, float
 
 /* Launch L clears the counters of launch L+1 (and, on the first pass of a
  * frame, the stats of the next frame). Nobody reads them during this launch. */
-__device__ __forceinline__ void clear_next_counters(const FrameParams& p)
+__device__ __forceinline__ void clear_next_stats(const FrameParams& p)
+{
+    if (blockIdx.x != 0 || p.pass != 0) return;
+    unsigned long long* a = p.ctr->stats[p.stats_set ^ 1u].active;
+    for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) a[i] = 0ull;
+}
+
+__device__ __forceinline__ void clear_next_counters(const FrameParams& p, bool stats_too = true)
 {
     if (blockIdx.x != 0) return;
     uint32_t* w = reinterpret_cast<uint32_t*>(&p.ctr->wave[p.wave_set ^ 1u]);
     for (uint32_t i = threadIdx.x; i < sizeof(WaveCounters) / 4; i += blockDim.x) w[i] = 0u;
-    if (p.pass == 0)
-    {
-        unsigned long long* a = p.ctr->stats[p.stats_set ^ 1u].active;
-        for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) a[i] = 0ull;
-    }
+    if (stats_too) clear_next_stats(p);
+}
+
+/* Wave-size forecast from the previous launch: bit b of the result is set when the rays
+ * traced at bounce b by the previous frame (pass 0; earlier passes of this frame otherwise)
+ * fit the in-thread tail (<= tail_threshold per pass). A wave whose successor is forecast
+ * that small lets its few survivors run on inside their threads instead of queueing them,
+ * which saves the grid barrier and the tail wave behind it. Scheduling only: a wrong
+ * forecast (camera or scene just changed) costs lane utilisation for one frame, never a
+ * different result. Must run before the first grid barrier (the stats set it reads is
+ * zeroed for the next frame right after that). */
+__device__ __forceinline__ unsigned long long forecast_small_waves(const FrameParams& p)
+{
+    if (!p.use_forecast) return 0ull;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long* a =
+        p.pass == 0 ? p.ctr->stats[p.stats_set ^ 1u].active : p.ctr->stats[p.stats_set].active;
+    const unsigned long long div = p.pass == 0 ? (unsigned long long)p.aa : (unsigned long long)p.pass;
+    const unsigned long long lim = (unsigned long long)p.tail_threshold * div;
+    const uint32_t lo = __ballot_sync(0xFFFFFFFFu, a[lane] <= lim);
+    const uint32_t hi = __ballot_sync(0xFFFFFFFFu, a[lane + 32u] <= lim);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
@@ -743,6 +767,29 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
     if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
 }
 
+/* Resolve a claim issued earlier on `shard` of the sharded global work counters `ctr` into a unit
+ * index; a dry shard is left for the next one that still has work (see primary_phase).
+ * 0xFFFFFFFF: no primary chunk is left anywhere. */
+__device__ __forceinline__ uint32_t resolve_claim(uint32_t* ctr, uint32_t n_units, uint32_t& shard,
+                                                  uint32_t claim)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+    while (unit >= n_units)
+    {
+        uint32_t v = 0xFFFFFFFFu;
+        if (lane < RVPT_CHUNK_SHARDS) v = *reinterpret_cast<volatile uint32_t*>(&ctr[lane * 32u]);
+        const bool has_work = lane < RVPT_CHUNK_SHARDS && (uint64_t)v * RVPT_CHUNK_SHARDS + lane < n_units;
+        const uint32_t live = __ballot_sync(0xFFFFFFFFu, has_work);
+        if (live == 0) return 0xFFFFFFFFu;
+        const uint32_t rot = (live >> (shard + 1u)) | (live << (RVPT_CHUNK_SHARDS - 1u - shard));
+        shard = (shard + 1u + (uint32_t)(__ffs(rot & 0xFFFFu) - 1)) % RVPT_CHUNK_SHARDS;
+        if (lane == 0) claim = atomicAdd(&ctr[shard * 32u], 1u);
+        unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
+    }
+    return unit;
+}
+
 __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathState& s,
                                           uint32_t& slot)
 {
@@ -772,8 +819,8 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
  *             later bounces are counted as they are traced.
  */
 #define RVPT_WAVE_SPREAD 1u
-#define RVPT_WAVE_IN_THREAD 2u
-template <bool kSmem, bool kOct>
+#define RVPT_WAVE_SHARDED 4u /* big wave, every 32-ray group claimed from the sharded counters */
+template <bool kSmem, bool kOct, bool kInThread>
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
                                              uint32_t count, uint32_t mode)
 {
@@ -783,7 +830,10 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long* active = p.ctr->stats[p.stats_set].active;
     const bool spread = (mode & RVPT_WAVE_SPREAD) != 0;
-    const bool in_thread = (mode & RVPT_WAVE_IN_THREAD) != 0;
+    constexpr bool in_thread = kInThread; /* compile-time: keeps the queueing call sites lean */
+    const bool sharded = (mode & RVPT_WAVE_SHARDED) != 0 && !spread;
+    uint32_t* shard_ctr = wc.bounce_ctr[b & 1];
+    uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     /* spread: L lanes per warp and round; otherwise full 32-ray groups, 7/8 of
@@ -796,11 +846,24 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     const uint32_t dyn_base = static_rounds * n_warps;
 
     uint32_t claim = 0;
-    if (static_rounds == 0 && lane == 0) claim = atomicAdd(&wc.work_ctr[b], 1u);
+    if (sharded)
+    {
+        if (lane == 0) claim = atomicAdd(&shard_ctr[shard * 32u], 1u);
+    }
+    else if (static_rounds == 0 && lane == 0)
+        claim = atomicAdd(&wc.work_ctr[b], 1u);
     for (uint32_t round = 0;; ++round)
     {
         uint32_t g;
-        if (round < static_rounds)
+        if (sharded)
+        {
+            /* same scheme as the primary wave: the measured barrier wait of a 7/8-static wave
+             * was three times that of the fully dynamic primary wave */
+            g = resolve_claim(shard_ctr, groups, shard, claim);
+            if (g == 0xFFFFFFFFu) break;
+            if (lane == 0) claim = atomicAdd(&shard_ctr[shard * 32u], 1u);
+        }
+        else if (round < static_rounds)
             g = round * n_warps + gwarp;
         else if (spread)
             break;
@@ -811,7 +874,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             if (spread) continue; /* other warps of this round still have rays; warp-uniform */
             break;
         }
-        if (!spread && round + 1 >= static_rounds && lane == 0)
+        if (!sharded && !spread && round + 1 >= static_rounds && lane == 0)
             claim = atomicAdd(&wc.work_ctr[b], 1u);
 
         const uint32_t i = g * L + lane;
@@ -941,8 +1004,17 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     __shared__ uint64_t bar;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 
+    __shared__ unsigned long long small_waves;
+
     stamp(p, 0);
-    clear_next_counters(p);
+    /* with bounce waves, the next frame's stats set is zeroed after the first grid barrier:
+     * until then it still holds the previous frame's counts, which the forecast reads */
+    clear_next_counters(p, p.max_bounces < 2);
+    if (threadIdx.x < 32)
+    {
+        const unsigned long long m = forecast_small_waves(p);
+        if (threadIdx.x == 0) small_waves = m;
+    }
     const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);
     stamp(p, 1);
 
@@ -953,6 +1025,7 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     for (int b = 1; b < p.max_bounces; ++b)
     {
         grid.sync(); /* wave b-1 is complete: its survivor count is final */
+        if (b == 1) clear_next_stats(p);
         stamp(p, 2 * b + 1);
         const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&wc.qcount[b - 1]);
         if (count == 0) break;
@@ -961,11 +1034,24 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         if (count <= p.tail_threshold)
         {
-            bounce_phase<kSmem, kOct>(p, sc, b, count, RVPT_WAVE_SPREAD | RVPT_WAVE_IN_THREAD);
+            bounce_phase<kSmem, kOct, true>(p, sc, b, count, RVPT_WAVE_SPREAD);
             stamp(p, 2 * b + 2);
             break;
         }
-        bounce_phase<kSmem, kOct>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+        /* wave b claims from counter set b & 1; the other set (last used by wave b-1, which is
+         * complete) is zeroed now for wave b+1 — the grid barrier orders it */
+        if (blockIdx.x == 0)
+            for (uint32_t i = threadIdx.x; i < RVPT_CHUNK_SHARDS * 32u; i += blockDim.x)
+                wc.bounce_ctr[(b + 1) & 1][i] = 0u;
+        const uint32_t deal = count <= 64u * n_warps ? RVPT_WAVE_SPREAD : RVPT_WAVE_SHARDED;
+        if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull) && !(p.flags & 0x40000000u))
+        {
+            /* forecast: wave b+1 would be a tail anyway — its rays finish here, in their threads */
+            bounce_phase<kSmem, kOct, true>(p, sc, b, count, deal);
+            stamp(p, 2 * b + 2);
+            break;
+        }
+        bounce_phase<kSmem, kOct, false>(p, sc, b, count, deal);
         stamp(p, 2 * b + 2);
     }
 }
@@ -1073,30 +1159,6 @@ __device__ __forceinline__ void flow_retire(FlowShared& fs)
     if ((threadIdx.x & 31u) == 0) atomicSub(&fs.active, 1u); /* after this warp's commits, in program order */
 }
 
-/* Resolve a claim issued earlier on `shard` of the sharded global chunk counters into a chunk
- * index; a dry shard is left for the next one that still has work (see primary_phase).
- * 0xFFFFFFFF: no primary chunk is left anywhere. */
-__device__ __forceinline__ uint32_t flow_resolve_claim(const FrameParams& p, WaveCounters& wc, uint32_t& shard,
-                                                       uint32_t claim)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_units = p.n_chunks;
-    uint32_t unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
-    while (unit >= n_units)
-    {
-        uint32_t v = 0xFFFFFFFFu;
-        if (lane < RVPT_CHUNK_SHARDS) v = *reinterpret_cast<volatile uint32_t*>(&wc.chunk_ctr[lane * 32u]);
-        const bool has_work = lane < RVPT_CHUNK_SHARDS && (uint64_t)v * RVPT_CHUNK_SHARDS + lane < n_units;
-        const uint32_t live = __ballot_sync(0xFFFFFFFFu, has_work);
-        if (live == 0) return 0xFFFFFFFFu;
-        const uint32_t rot = (live >> (shard + 1u)) | (live << (RVPT_CHUNK_SHARDS - 1u - shard));
-        shard = (shard + 1u + (uint32_t)(__ffs(rot & 0xFFFFu) - 1)) % RVPT_CHUNK_SHARDS;
-        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
-        unit = __shfl_sync(0xFFFFFFFFu, claim, 0) * RVPT_CHUNK_SHARDS + shard;
-    }
-    return unit;
-}
-
 template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT<kSmem>& sc, FlowShared& fs)
 {
@@ -1188,7 +1250,7 @@ __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT
 
         if (kind == FLOW_PRIMARY)
         {
-            const uint32_t c = flow_resolve_claim(p, wc, shard, claim);
+            const uint32_t c = resolve_claim(wc.chunk_ctr, p.n_chunks, shard, claim);
             if (c == 0xFFFFFFFFu)
             {
                 holding = false; /* this warp only pops from now on */
@@ -1370,7 +1432,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     else
         sc = make_view<false>(p.scene, p.layout);
     const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-    bounce_phase<kSmem, false>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+    bounce_phase<kSmem, false, false>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
 }
 
 /* ======================================================================== */
