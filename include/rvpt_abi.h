@@ -143,6 +143,10 @@ typedef struct rvpt_b200_stats
  * own wavefront queue instead of the whole grid synchronising between bounce
  * waves. Same results. */
 #define RVPT_B200_FLAG_FLOW 0x20u
+/* Do not use the previous frame's per-bounce ray counts to forecast tiny waves (k_frame
+ * then always queues survivors and pays the barrier + tail wave behind them). Same
+ * results; for A/B measurements. */
+#define RVPT_B200_FLAG_NO_FORECAST 0x40u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 

@@ -20,6 +20,7 @@ FLAG_BRUTE_FORCE = 0x4
 FLAG_UNFUSED = 0x8
 FLAG_NO_OCTANTS = 0x10
 FLAG_FLOW = 0x20
+FLAG_NO_FORECAST = 0x40
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 

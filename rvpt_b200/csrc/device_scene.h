@@ -14,6 +14,8 @@
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
 #define RVPT_FLOW_RING 4096u        /* k_flow: path records in one CTA's ring queue */
+/* octant node copies in shared memory: byte distance between the two float4 halves of a record */
+#define RVPT_OCT_B_OFFSET (100u * 1024u)
 #define RVPT_TIMELINE_SLOTS 16u     /* per-CTA phase stamps of the last frame kernel */
 
 /*

@@ -537,7 +537,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
-                  RVPT_B200_FLAG_FLOW | 0x40000000u /* reserved: A/B experiments */))
+                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     ctx->device = device;
     ctx->W = width;
@@ -721,7 +721,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     /* a wave with at most two rays per resident warp runs to completion in its threads */
     p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * 2u;
     /* the previous frame's per-bounce counts forecast this frame's small waves (k_frame) */
-    p.use_forecast = (!unfused && ctx->frame_seq > 0) ? 1u : 0u;
+    p.use_forecast = (!unfused && ctx->frame_seq > 0 && !(ctx->flags & RVPT_B200_FLAG_NO_FORECAST)) ? 1u : 0u;
 
     uint32_t launches = 0;
     for (int pass = 0; pass < rs->aa && p.n_chunks > 0; ++pass)

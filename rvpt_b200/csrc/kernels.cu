@@ -140,7 +140,10 @@ struct SceneViewT
     addr_t rel_num;
     /* kOct only: eight copies of the node array, one per ray-direction octant, with
      * each axis' two bounds stored (near, far) for that octant — and eight more relative
-     * to the camera origin for the primary wave. oct_stride = n_nodes * 32 bytes. */
+     * to the camera origin for the primary wave. Each copy is split into two float4 arrays
+     * (16-byte stride: incoherent rays then spread over all 32 banks instead of half of them):
+     * (near x, far x, near y, far y) at oct_nodes + copy * oct_stride + node * 16 and
+     * (near z, far z, skip, leaf) RVPT_OCT_B_OFFSET bytes further. oct_stride = n_nodes * 16. */
     addr_t oct_nodes;
     addr_t oct_rel_nodes;
     uint32_t oct_stride;
@@ -159,6 +162,17 @@ __device__ __forceinline__ float4 ld_f4(A base, uint32_t idx)
     }
     else
         return __ldg(reinterpret_cast<const float4*>(base) + idx);
+}
+
+/* shared-memory float4 at byte address `addr + kOff` (compile-time offset: same address register) */
+template <uint32_t kOff>
+__device__ __forceinline__ float4 lds_f4_off(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr), "n"(kOff));
+    return v;
 }
 
 template <bool kSmem, typename A>
@@ -252,8 +266,18 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
-        const float4 n0 = ld_f4<kSmem>(nodes, 2 * node);
-        const float4 n1 = ld_f4<kSmem>(nodes, 2 * node + 1);
+        float4 n0, n1;
+        if constexpr (kSorted)
+        {
+            const uint32_t a = (uint32_t)nodes + node * 16u;
+            n0 = lds_f4_off<0>(a);
+            n1 = lds_f4_off<RVPT_OCT_B_OFFSET>(a);
+        }
+        else
+        {
+            n0 = ld_f4<kSmem>(nodes, 2 * node);
+            n1 = ld_f4<kSmem>(nodes, 2 * node + 1);
+        }
         float fx, nx, fy, ny, fz, nz;
         if (kRel)
         {
@@ -954,27 +978,28 @@ __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, u
         {
             static_assert(kWarpsPerCta % 8 == 0, "one warp group per octant");
             float4* oct = reinterpret_cast<float4*>(extra);
-            float4* oct_rel = oct + 16 * (size_t)n_nodes;
+            float4* oct_rel = oct + 8 * (size_t)n_nodes;
             const uint32_t w = threadIdx.x >> 5, k = w & 7u;
-            float4* dst = oct + 2 * (size_t)n_nodes * k;
-            float4* dst_rel = oct_rel + 2 * (size_t)n_nodes * k;
+            float4* dst = oct + (size_t)n_nodes * k;
+            float4* dst_rel = oct_rel + (size_t)n_nodes * k;
+            constexpr uint32_t kB = RVPT_OCT_B_OFFSET / 16u; /* second half of every record */
             for (uint32_t i = (w >> 3) * 32u + (threadIdx.x & 31u); i < n_nodes; i += (kWarpsPerCta / 8) * 32u)
             {
                 const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
                 const float ax = (k & 1u) ? n0.y : n0.x, bx = (k & 1u) ? n0.x : n0.y;
                 const float ay = (k & 2u) ? n0.w : n0.z, by = (k & 2u) ? n0.z : n0.w;
                 const float az = (k & 4u) ? n1.y : n1.x, bz = (k & 4u) ? n1.x : n1.y;
-                dst[2 * i] = make_float4(ax, bx, ay, by);
-                dst[2 * i + 1] = make_float4(az, bz, n1.z, n1.w);
+                dst[i] = make_float4(ax, bx, ay, by);
+                dst[i + kB] = make_float4(az, bz, n1.z, n1.w);
                 if constexpr (kRel)
                 {
-                    dst_rel[2 * i] = make_float4(ax - o.x, bx - o.x, ay - o.y, by - o.y);
-                    dst_rel[2 * i + 1] = make_float4(az - o.z, bz - o.z, n1.z, n1.w);
+                    dst_rel[i] = make_float4(ax - o.x, bx - o.x, ay - o.y, by - o.y);
+                    dst_rel[i + kB] = make_float4(az - o.z, bz - o.z, n1.z, n1.w);
                 }
             }
             sc.oct_nodes = smem_u32(oct);
             sc.oct_rel_nodes = smem_u32(oct_rel);
-            sc.oct_stride = n_nodes * 32u;
+            sc.oct_stride = n_nodes * 16u;
         }
         else if constexpr (kRel)
         {
@@ -1044,7 +1069,7 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
             for (uint32_t i = threadIdx.x; i < RVPT_CHUNK_SHARDS * 32u; i += blockDim.x)
                 wc.bounce_ctr[(b + 1) & 1][i] = 0u;
         const uint32_t deal = count <= 64u * n_warps ? RVPT_WAVE_SPREAD : RVPT_WAVE_SHARDED;
-        if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull) && !(p.flags & 0x40000000u))
+        if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull))
         {
             /* forecast: wave b+1 would be a tail anyway — its rays finish here, in their threads */
             bounce_phase<kSmem, kOct, true>(p, sc, b, count, deal);
@@ -1237,7 +1262,7 @@ __device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT
         if (kind == FLOW_RETRY) continue;
         /* acquire side of the commit counters: the records of a popped group were released
          * by their writers' fence + shared-memory atomic */
-        if ((kind == FLOW_POP || kind == FLOW_POP_TAIL) && !(p.flags & 0x40000000u)) fence_cta();
+        if (kind == FLOW_POP || kind == FLOW_POP_TAIL) fence_cta();
         if (kind == FLOW_WAIT)
         {
             /* Waiting warps must not take issue slots from the warps they wait for: sleep with
@@ -1901,7 +1926,10 @@ size_t frame_smem_bytes(size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris, b
     /* blob + one float per triangle + the derived node copies: 8 absolute + 8
      * origin-relative octant copies, or one origin-relative copy */
     const size_t rel_num = ((size_t)n_tris * 4u + 15u) & ~(size_t)15u;
-    return scene_bytes + rel_num + (size_t)n_nodes * 32u * (oct ? 16u : 1u);
+    if (!oct) return scene_bytes + rel_num + (size_t)n_nodes * 32u;
+    /* 16 copies of the first record halves, and the second halves RVPT_OCT_B_OFFSET further */
+    if ((size_t)n_nodes * 16u * 16u > RVPT_OCT_B_OFFSET) return ~(size_t)0; /* does not fit: no octant copies */
+    return scene_bytes + rel_num + RVPT_OCT_B_OFFSET + (size_t)n_nodes * 16u * 16u;
 }
 
 cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bounce_ctas_per_sm,

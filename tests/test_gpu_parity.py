@@ -571,3 +571,28 @@ def test_flow_kernel_sizes_and_partition(rv, oracle_mod, builtin, size):
             part.render_frame(rv.default_settings(frame=f), cam)
         acc += part.read_accum_f32()
     _assert_bit_equal(acc, full, "flow kernel, 3-way partition")
+
+
+def test_wave_forecast_is_scheduling_only(rv, oracle_mod, builtin):
+    """k_frame lets the survivors of a wave run on in their threads when the previous frame
+    says the next wave would be tiny. The pinned pose has such waves ([.., 3963, 345, 64, ..]
+    at 256x256); moving the camera between frames makes the forecast wrong on purpose. Images
+    and per-bounce counts equal the oracle's with and without the forecast."""
+    from rvpt_b200 import _lib
+    W = H = 256
+    poses = [PINNED_POSE, PINNED_POSE, PINNED_POSE, DEFAULT_POSE, DEFAULT_POSE, PINNED_POSE]
+    for flags in (0, _lib.FLAG_NO_FORECAST):
+        eng = rv.Engine(W, H, flags=flags)
+        eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+        ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+        frame = 0
+        for i, pose in enumerate(poses):
+            if i and pose != poses[i - 1]:
+                frame = 0  # rvpt.cpp:102-107: a camera change restarts the accumulation
+            cam = rv.camera_data(translation=pose, aspect=W / H)
+            rs = rv.default_settings(frame=frame)
+            eng.render_frame(rs, cam)
+            ora.render_frame(rs, cam)
+            assert eng.stats()["active"] == ora.active_list(), (flags, i)
+            frame += 1
+        _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"forecast flags={flags}")

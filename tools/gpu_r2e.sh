@@ -1,11 +1,11 @@
 #!/bin/bash
-# sharded dynamic bounce waves: all tests, A/B bench (new default vs 0x40000000 = old static dealing), timeline
+# sharded dynamic bounce waves: all tests, A/B bench (new default vs 0x40 = old static dealing), timeline
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 for v in fcast nofcast; do
   case $v in
     fcast) unset RVPT_B200_EXTRA_FLAGS;;
-    nofcast) export RVPT_B200_EXTRA_FLAGS=0x40000000;;
+    nofcast) export RVPT_B200_EXTRA_FLAGS=0x40;;
   esac
   timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${v}_n1.json 2> gpurun_out/bench_${v}_n1.err
   timeout 300 python bench.py --steps 30 --warmup 3 --pose pinned --no-cpu-baseline > gpurun_out/bench_${v}_pinned.json 2>/dev/null
