@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,6 +47,7 @@ struct rvpt_b200_ctx
     int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
     int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
     int grid_frame = 0, grid_primary = 0, grid_bounce = 0, grid_flow = 0;
+    uint32_t tail_rays_per_warp = 16; /* waves up to this many rays per resident warp finish in-thread (measured: 2..8 equal, 16 saves a barrier + wave on sparse poses) */
     uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
     uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
 
@@ -539,6 +541,8 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
                   RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
+    if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
+        ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
     ctx->device = device;
     ctx->W = width;
     ctx->H = height;
@@ -719,7 +723,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.stats_set = ctx->frame_seq & 1u;
     const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;
     /* a wave with at most two rays per resident warp runs to completion in its threads */
-    p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * 2u;
+    p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * ctx->tail_rays_per_warp;
     /* the previous frame's per-bounce counts forecast this frame's small waves (k_frame) */
     p.use_forecast = (!unfused && ctx->frame_seq > 0 && !(ctx->flags & RVPT_B200_FLAG_NO_FORECAST)) ? 1u : 0u;
 
