@@ -204,7 +204,7 @@ def displaced_sphere_scene(n_triangles: int = 20000, seed: int = 1) -> Scene:
     main.cpp and cannot travel to the GPU box): a UV sphere of radius ~1 at
     (0, 1, 0) with smooth radial displacement, ~n_triangles triangles, three
     Lambert materials in latitude bands, over a large ground quad. Scenes whose
-    device blob exceeds 192 KB take the L2-resident (non-shared-memory) kernel path."""
+    device blob (plus its derived copies) exceeds the 224 KB shared-memory budget take the L2-resident (non-shared-memory) kernel path."""
     nv = max(4, int(round((n_triangles / 4.0) ** 0.5)))
     nu = 2 * nv
     u = np.linspace(0.0, 2.0 * np.pi, nu + 1)[:-1]
