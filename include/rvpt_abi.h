@@ -103,7 +103,7 @@ typedef struct rvpt_b200_stats
     uint64_t segments;                             /* intersect_scene calls = sum of active[] */
     uint64_t active[RVPT_MAX_BOUNCE_STATS];        /* rays traced at bounce b */
     uint32_t kernel_launches;                      /* kernels launched for the frame */
-    uint32_t reserved;
+    uint32_t traversal_order;                      /* 0 reference child order, 1 front to back (see REFERENCE_ORDER) */
 } rvpt_b200_stats;
 
 /* ------------------------------------------------------------------------ */
@@ -147,6 +147,14 @@ typedef struct rvpt_b200_stats
  * then always queues survivors and pays the barrier + tail wave behind them). Same
  * results; for A/B measurements. */
 #define RVPT_B200_FLAG_NO_FORECAST 0x40u
+/* Walk every BVH in the reference's child order (first, first+1: intersection.glsl:402-406).
+ * By default small scenes WITHOUT coincident faces (two coplanar triangles overlapping with
+ * positive area, checked at upload) are walked front to back per ray-direction octant: the
+ * nearest accepted hit then does not depend on the visiting order (SURVEY.md §8c "BVH
+ * dependence"; the parity tests hold both orders to the oracle bit for bit). Scenes with
+ * coincident faces — where the strict `t < closest_t` lets the first triangle visited win —
+ * always keep the reference's order. rvpt_b200_stats.traversal_order reports the choice. */
+#define RVPT_B200_FLAG_REFERENCE_ORDER 0x80u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 
@@ -316,6 +324,17 @@ RVPT_API int rvpt_b200_build_bvh(const rvpt_triangle* triangles, size_t n_triang
  * fov in degrees. Writes the 80-byte block. */
 RVPT_API void rvpt_b200_camera_data(const float translation[3], const float rotation_deg[3],
                                     float aspect, float fov_deg, float scale, float out[20]);
+
+/* Host only: 1 if two triangles of the list are coplanar and overlap with positive area. */
+RVPT_API int rvpt_b200_has_coincident_faces(const rvpt_triangle* triangles, size_t n_triangles);
+
+/* Test / tooling hook (host only): the eight front-to-back octant node arrays the engine
+ * uploads next to a scene (device_scene.h). out = 8*n float4 (near x, far x, near y, far y)
+ * followed by 8*n float4 (near z, far z, skip link, first triangle | 0xFFFFFFFF) with
+ * n = *n_packed_nodes; pass out = NULL to query n. */
+RVPT_API int rvpt_b200_octant_layouts(const rvpt_bvh_node* nodes, size_t n_nodes,
+                                      const rvpt_triangle* triangles, size_t n_triangles, float* out,
+                                      size_t capacity_floats, size_t* n_packed_nodes);
 
 /* ABI / build self-description. */
 RVPT_API uint32_t rvpt_b200_abi_version(void);

@@ -21,6 +21,7 @@ FLAG_UNFUSED = 0x8
 FLAG_NO_OCTANTS = 0x10
 FLAG_FLOW = 0x20
 FLAG_NO_FORECAST = 0x40
+FLAG_REFERENCE_ORDER = 0x80
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -31,7 +32,7 @@ class Stats(C.Structure):
         ("segments", C.c_uint64),
         ("active", C.c_uint64 * MAX_BOUNCE_STATS),
         ("kernel_launches", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("traversal_order", C.c_uint32),
     ]
 
 
@@ -86,6 +87,9 @@ SIGNATURES = {
                                       C.c_void_p]),
     "rvpt_b200_camera_data": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                      C.c_void_p]),
+    "rvpt_b200_has_coincident_faces": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "rvpt_b200_octant_layouts": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                           C.c_size_t, C.POINTER(C.c_size_t)]),
     "rvpt_b200_abi_version": (C.c_uint32, []),
     "rvpt_b200_build_info": (C.c_char_p, []),
     "rvpt_b200_selftest_math": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -65,6 +65,7 @@ struct DevMaterial
  * The whole scene is one contiguous 16-byte-aligned blob so one TMA bulk copy
  * (cp.async.bulk) stages it into shared memory:
  *   [DevNode x n_nodes][DevTri x n_tris][meta u32 x n_tris (padded)][DevMaterial x n_mats]
+ *   [ordered octant node arrays, optional]
  */
 struct SceneLayout
 {
@@ -72,8 +73,13 @@ struct SceneLayout
     uint32_t off_tris;  /* byte offsets inside the blob */
     uint32_t off_meta;
     uint32_t off_mats;
-    uint32_t bytes;     /* multiple of 16 */
-    uint32_t pad;
+    uint32_t bytes;     /* of the part above (what the plain kernels stage), multiple of 16 */
+    /* Optional block behind it (0 = absent): the eight direction-octant node arrays in
+     * FRONT-TO-BACK order — for octant k every inner node's children are laid out so that the
+     * one lying earlier along the ray direction is visited first (its own pre-order numbering
+     * and skip links; leaves keep their DevTri ranges). Two float4 arrays of 8 * n_nodes
+     * entries: (near x, far x, near y, far y) then (near z, far z, skip, leaf). */
+    uint32_t off_oct;
 };
 
 /*

@@ -244,6 +244,7 @@ struct ScopedTimer
 struct PackedScene
 {
     bool bounds_ordered = true; /* every node has min <= max on every axis (no NaN) */
+    bool coincident_faces = false; /* has_coincident_faces(): the walk order can decide a hit */
     std::vector<DevNode> nodes;
     std::vector<DevTri> tris;
     std::vector<uint32_t> meta;
@@ -399,6 +400,144 @@ int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
     return 0;
 }
 
+/* Two triangles that lie in one plane and overlap with positive area are hit at (nearly) the
+ * same t by every ray through the overlap: which of them wins then depends on the order the
+ * BVH is walked in (strict `t < closest_t`, intersection.glsl:394: the first one visited), and
+ * so does whether the second one's box survives the closest_t clip. Such scenes — an object
+ * standing on a floor with its bottom face modelled — keep the reference's child order; scenes
+ * without such pairs have an order-independent nearest hit (up to last-bit coincidences that
+ * the reference's own result shares), and may be walked front to back. O(n^2) on purpose:
+ * only scenes small enough for the shared-memory path ask. */
+bool has_coincident_faces(const rvpt_triangle* tris, size_t n)
+{
+    struct Face
+    {
+        double v[3][3], nrm[3], d, scale;
+        bool degenerate;
+    };
+    std::vector<Face> f(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const float* src[3] = {tris[i].vertex0, tris[i].vertex1, tris[i].vertex2};
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) f[i].v[k][a] = src[k][a];
+        double e0[3], e1[3];
+        for (int a = 0; a < 3; ++a) e0[a] = f[i].v[1][a] - f[i].v[0][a], e1[a] = f[i].v[2][a] - f[i].v[0][a];
+        double c[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+        const double len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        f[i].degenerate = !(len > 0.0);
+        f[i].scale = 0.0;
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) f[i].scale = std::max(f[i].scale, std::fabs(f[i].v[k][a]));
+        if (f[i].degenerate) continue;
+        for (int a = 0; a < 3; ++a) f[i].nrm[a] = c[a] / len;
+        f[i].d = f[i].nrm[0] * f[i].v[0][0] + f[i].nrm[1] * f[i].v[0][1] + f[i].nrm[2] * f[i].v[0][2];
+    }
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (f[i].degenerate) continue;
+        for (size_t j = i + 1; j < n; ++j)
+        {
+            if (f[j].degenerate) continue;
+            const double eps = 1e-5 * std::max(1.0, std::max(f[i].scale, f[j].scale));
+            const double dp = f[i].nrm[0] * f[j].nrm[0] + f[i].nrm[1] * f[j].nrm[1] + f[i].nrm[2] * f[j].nrm[2];
+            if (std::fabs(dp) < 1.0 - 1e-9) continue; /* planes not parallel */
+            bool same_plane = true;
+            for (int k = 0; k < 3 && same_plane; ++k)
+            {
+                const double dist = f[i].nrm[0] * f[j].v[k][0] + f[i].nrm[1] * f[j].v[k][1] +
+                                    f[i].nrm[2] * f[j].v[k][2] - f[i].d;
+                same_plane = std::fabs(dist) <= eps;
+            }
+            if (!same_plane) continue;
+            /* 2-D separating-axis test in the plane (dominant axis dropped); touching along an
+             * edge or at a vertex (two halves of a quad) is not an overlap */
+            int drop = 0;
+            for (int a = 1; a < 3; ++a)
+                if (std::fabs(f[i].nrm[a]) > std::fabs(f[i].nrm[drop])) drop = a;
+            const int ax0 = (drop + 1) % 3, ax1 = (drop + 2) % 3;
+            double P[2][3][2];
+            for (int k = 0; k < 3; ++k)
+            {
+                P[0][k][0] = f[i].v[k][ax0], P[0][k][1] = f[i].v[k][ax1];
+                P[1][k][0] = f[j].v[k][ax0], P[1][k][1] = f[j].v[k][ax1];
+            }
+            bool separated = false;
+            for (int t = 0; t < 2 && !separated; ++t)
+                for (int e = 0; e < 3 && !separated; ++e)
+                {
+                    const double ex = P[t][(e + 1) % 3][0] - P[t][e][0], ey = P[t][(e + 1) % 3][1] - P[t][e][1];
+                    const double nx = -ey, ny = ex;
+                    const double nl = std::sqrt(nx * nx + ny * ny);
+                    if (!(nl > 0.0)) continue;
+                    double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+                    for (int q = 0; q < 2; ++q)
+                        for (int k = 0; k < 3; ++k)
+                        {
+                            const double pr = (P[q][k][0] * nx + P[q][k][1] * ny) / nl;
+                            lo[q] = std::min(lo[q], pr), hi[q] = std::max(hi[q], pr);
+                        }
+                    separated = hi[0] <= lo[1] + eps || hi[1] <= lo[0] + eps;
+                }
+            if (!separated) return true;
+        }
+    }
+    return false;
+}
+
+/* The eight front-to-back node arrays (device_scene.h, SceneLayout::off_oct) from the packed
+ * reference-order nodes. In pre-order a subtree is a contiguous range whose size does not
+ * depend on the order its children are visited in, so every layout reuses the reference
+ * layout's subtree sizes for its skip links. Children are ordered along the axis on which
+ * their box centres differ most; a tie keeps the reference's order. out = 8*n float4 of the
+ * first halves, then 8*n float4 of the second halves. */
+void build_octant_layouts(const std::vector<DevNode>& ref, std::vector<float>& out)
+{
+    const uint32_t n = (uint32_t)ref.size();
+    out.assign((size_t)n * 8u * 8u, 0.0f);
+    float* A = out.data();
+    float* B = out.data() + (size_t)n * 8u * 4u;
+    auto size_of = [&](uint32_t k) { return (ref[k].skip == RVPT_NODE_END ? n : ref[k].skip) - k; };
+    std::vector<uint32_t> todo;
+    for (uint32_t oct = 0; oct < 8; ++oct)
+    {
+        const float sgn[3] = {(oct & 1u) ? -1.0f : 1.0f, (oct & 2u) ? -1.0f : 1.0f, (oct & 4u) ? -1.0f : 1.0f};
+        uint32_t idx = 0;
+        todo.clear();
+        todo.push_back(0u);
+        while (!todo.empty())
+        {
+            const uint32_t k = todo.back();
+            todo.pop_back();
+            const DevNode& d = ref[k];
+            const uint32_t total = size_of(k);
+            const uint32_t skip = idx + total < n ? idx + total : RVPT_NODE_END;
+            float* a = A + ((size_t)oct * n + idx) * 4u;
+            float* b = B + ((size_t)oct * n + idx) * 4u;
+            a[0] = (oct & 1u) ? d.bmax_x : d.bmin_x, a[1] = (oct & 1u) ? d.bmin_x : d.bmax_x;
+            a[2] = (oct & 2u) ? d.bmax_y : d.bmin_y, a[3] = (oct & 2u) ? d.bmin_y : d.bmax_y;
+            b[0] = (oct & 4u) ? d.bmax_z : d.bmin_z, b[1] = (oct & 4u) ? d.bmin_z : d.bmax_z;
+            std::memcpy(&b[2], &skip, 4);
+            std::memcpy(&b[3], &d.leaf_first, 4);
+            ++idx;
+            if (d.leaf_first == RVPT_NODE_INNER)
+            {
+                const uint32_t c0 = k + 1u, c1 = c0 + size_of(c0);
+                const DevNode &p = ref[c0], &q = ref[c1];
+                const float diff[3] = {(q.bmin_x + q.bmax_x) - (p.bmin_x + p.bmax_x),
+                                       (q.bmin_y + q.bmax_y) - (p.bmin_y + p.bmax_y),
+                                       (q.bmin_z + q.bmax_z) - (p.bmin_z + p.bmax_z)};
+                int ax = 0;
+                for (int t = 1; t < 3; ++t)
+                    if (std::fabs(diff[t]) > std::fabs(diff[ax])) ax = t;
+                const bool c0_first = diff[ax] * sgn[ax] >= 0.0f; /* c1 lies further along the ray */
+                todo.push_back(c0_first ? c1 : c0); /* popped second */
+                todo.push_back(c0_first ? c0 : c1);
+            }
+        }
+    }
+}
+
 /* A scene too large for shared memory is traversed out of L2 (kSmem = false): pin its blob
  * there with an access-policy window so the path-state streams (hundreds of MB per frame)
  * do not evict it. Best effort: failures only cost performance. */
@@ -444,8 +583,19 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     off = align16(off + ps.mats.size() * sizeof(DevMaterial));
     if (off > 0xFFFFFFF0u) return fail(ctx, RVPT_B200_EUNSUPPORTED, "scene larger than 4 GiB");
     L.bytes = (uint32_t)off;
+    const bool oct = !(ctx->flags & RVPT_B200_FLAG_NO_OCTANTS) && ps.bounds_ordered &&
+                     rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris, true) <= RVPT_SMEM_SCENE_LIMIT;
+    std::vector<float> oct_block;
+    if (oct && !(ctx->flags & RVPT_B200_FLAG_REFERENCE_ORDER) && !ps.coincident_faces)
+    {
+        build_octant_layouts(ps.nodes, oct_block);
+        L.off_oct = L.bytes;
+    }
+    const size_t blob_bytes = (size_t)L.bytes + oct_block.size() * sizeof(float);
 
-    std::vector<unsigned char> blob(L.bytes, 0);
+    std::vector<unsigned char> blob(blob_bytes, 0);
+    if (!oct_block.empty())
+        std::memcpy(blob.data() + L.off_oct, oct_block.data(), oct_block.size() * sizeof(float));
     std::memcpy(blob.data(), ps.nodes.data(), ps.nodes.size() * sizeof(DevNode));
     std::memcpy(blob.data() + L.off_tris, ps.tris.data(), ps.tris.size() * sizeof(DevTri));
     std::memcpy(blob.data() + L.off_meta, ps.meta.data(), ps.meta.size() * sizeof(uint32_t));
@@ -457,7 +607,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
      * are large enough, the copy is ordered on the ctx stream behind the frames that still
      * read the old blob (no host synchronisation before it), and launch geometry is only
      * re-derived when the blob's shape changes. */
-    if (L.bytes > ctx->scene_capacity)
+    if (blob_bytes > ctx->scene_capacity)
     {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_scene);
@@ -465,20 +615,18 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
         ctx->d_scene = nullptr;
         ctx->h_scene_pinned = nullptr;
         ctx->scene_capacity = 0;
-        const size_t cap = ((size_t)L.bytes + 4095) & ~(size_t)4095;
+        const size_t cap = (blob_bytes + 4095) & ~(size_t)4095;
         CU(cudaMalloc(&ctx->d_scene, cap));
         CU(cudaMallocHost(&ctx->h_scene_pinned, cap));
         ctx->scene_capacity = cap;
     }
     else
         CU(cudaEventSynchronize(ctx->scene_copied)); /* the previous upload has left the staging copy */
-    std::memcpy(ctx->h_scene_pinned, blob.data(), L.bytes);
-    CU(cudaMemcpyAsync(ctx->d_scene, ctx->h_scene_pinned, L.bytes, cudaMemcpyHostToDevice,
+    std::memcpy(ctx->h_scene_pinned, blob.data(), blob_bytes);
+    CU(cudaMemcpyAsync(ctx->d_scene, ctx->h_scene_pinned, blob_bytes, cudaMemcpyHostToDevice,
                        ctx->stream));
     CU(cudaEventRecord(ctx->scene_copied, ctx->stream));
 
-    const bool oct = !(ctx->flags & RVPT_B200_FLAG_NO_OCTANTS) && ps.bounds_ordered &&
-                     rvpt::frame_smem_bytes(L.bytes, L.n_nodes, L.n_tris, true) <= RVPT_SMEM_SCENE_LIMIT;
     const bool same_shape = ctx->have_scene && L.bytes == ctx->layout.bytes &&
                             L.n_nodes == ctx->layout.n_nodes && L.n_tris == ctx->layout.n_tris &&
                             oct == ctx->scene_oct;
@@ -539,7 +687,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
-                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST))
+                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
@@ -648,6 +796,12 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
         rc = pack_scene(ctx, nodes, n_nodes, triangles, n_triangles, materials, n_materials, brute,
                         ps);
     if (rc) return rc;
+    /* front-to-back walking needs an order-independent nearest hit; only small scenes can use it */
+    if (!(ctx->flags & (RVPT_B200_FLAG_REFERENCE_ORDER | RVPT_B200_FLAG_NO_OCTANTS | RVPT_B200_FLAG_BRUTE_FORCE)) &&
+        n_triangles <= 4096)
+        ps.coincident_faces = has_coincident_faces(triangles, n_triangles);
+    else
+        ps.coincident_faces = true;
     return upload_packed(ctx, ps);
 }
 
@@ -908,6 +1062,7 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     }
     out->samples = ctx->last_max_bounces > 0 ? h.active[0] : 0;
     out->kernel_launches = ctx->last_launches;
+    out->traversal_order = ctx->layout.off_oct != 0u ? 1u : 0u;
     return 0;
 }
 
@@ -1055,6 +1210,33 @@ extern "C" int rvpt_b200_attach_output(rvpt_b200_ctx* ctx, const unsigned char h
     void* ptr = nullptr;
     CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_out_raster = (uchar4*)ptr;
+    return 0;
+}
+
+extern "C" int rvpt_b200_has_coincident_faces(const rvpt_triangle* triangles, size_t n_triangles)
+{
+    if (!triangles) return RVPT_B200_EINVAL;
+    return has_coincident_faces(triangles, n_triangles) ? 1 : 0;
+}
+
+extern "C" int rvpt_b200_octant_layouts(const rvpt_bvh_node* nodes, size_t n_nodes,
+                                        const rvpt_triangle* triangles, size_t n_triangles,
+                                        float* out, size_t capacity_floats, size_t* n_packed_nodes)
+{
+    if (!nodes || !triangles || !n_packed_nodes) return RVPT_B200_EINVAL;
+    /* one dummy material: pack_scene only validates indices against the count */
+    std::vector<rvpt_triangle> tris(triangles, triangles + n_triangles);
+    for (auto& t : tris) t.material_id[0] = 0.0f;
+    rvpt_material mat{};
+    PackedScene ps;
+    const int rc = pack_scene(nullptr, nodes, n_nodes, tris.data(), n_triangles, &mat, 1, false, ps);
+    if (rc) return rc;
+    *n_packed_nodes = ps.nodes.size();
+    if (!out) return 0;
+    std::vector<float> block;
+    build_octant_layouts(ps.nodes, block);
+    if (capacity_floats < block.size()) return RVPT_B200_EINVAL;
+    std::memcpy(out, block.data(), block.size() * sizeof(float));
     return 0;
 }
 

@@ -100,17 +100,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 /* Stage the scene blob into shared memory: one elected thread arms the
  * mbarrier with the byte count and issues the bulk copies (<= 32 KB each);
  * everybody waits on the barrier phase. */
+__device__ __forceinline__ void tma_region(void* dst, const unsigned char* src, uint32_t bytes, uint64_t* bar)
+{
+    for (uint32_t off = 0; off < bytes; off += 32768u)
+    {
+        uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        tma_bulk_g2s(static_cast<unsigned char*>(dst) + off, src + off, n, bar);
+    }
+}
+
+/* oct_a / oct_b: shared-memory destinations of the two halves of the front-to-back octant
+ * arrays that follow the blob in global memory (oct_bytes each; 0 = none). */
 __device__ __forceinline__ void stage_scene(unsigned char* smem_blob, uint64_t* bar,
-                                            const unsigned char* gmem_blob, uint32_t bytes)
+                                            const unsigned char* gmem_blob, uint32_t bytes,
+                                            void* oct_a = nullptr, void* oct_b = nullptr,
+                                            uint32_t oct_bytes = 0)
 {
     if (threadIdx.x == 0)
     {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768u)
+        mbar_expect_tx(bar, bytes + 2u * oct_bytes);
+        tma_region(smem_blob, gmem_blob, bytes, bar);
+        if (oct_bytes)
         {
-            uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-            tma_bulk_g2s(smem_blob + off, gmem_blob + off, n, bar);
+            tma_region(oct_a, gmem_blob + bytes, oct_bytes, bar);
+            tma_region(oct_b, gmem_blob + bytes + oct_bytes, oct_bytes, bar);
         }
     }
     __syncthreads();
@@ -682,16 +696,27 @@ __device__ __forceinline__ void clear_next_counters(const FrameParams& p, bool s
  * forecast (camera or scene just changed) costs lane utilisation for one frame, never a
  * different result. Must run before the first grid barrier (the stats set it reads is
  * zeroed for the next frame right after that). */
-__device__ __forceinline__ unsigned long long forecast_small_waves(const FrameParams& p)
+__device__ __forceinline__ unsigned long long forecast_small_waves(const FrameParams& p, uint32_t* mostly_hits)
 {
+    *mostly_hits = 0u;
     if (!p.use_forecast) return 0ull;
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned long long* a =
         p.pass == 0 ? p.ctr->stats[p.stats_set ^ 1u].active : p.ctr->stats[p.stats_set].active;
     const unsigned long long div = p.pass == 0 ? (unsigned long long)p.aa : (unsigned long long)p.pass;
     const unsigned long long lim = (unsigned long long)p.tail_threshold * div;
-    const uint32_t lo = __ballot_sync(0xFFFFFFFFu, a[lane] <= lim);
-    const uint32_t hi = __ballot_sync(0xFFFFFFFFu, a[lane + 32u] <= lim);
+    const unsigned long long a_lo = a[lane], a_hi = a[lane + 32u];
+    const uint32_t lo = __ballot_sync(0xFFFFFFFFu, a_lo <= lim);
+    const uint32_t hi = __ballot_sync(0xFFFFFFFFu, a_hi <= lim);
+    /* bounce rays (depth >= 1) against those that hit and went on (depth >= 2) */
+    unsigned long long rays = (lane >= 1u ? a_lo : 0ull) + a_hi, hits = (lane >= 2u ? a_lo : 0ull) + a_hi;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, d);
+        hits += __shfl_xor_sync(0xFFFFFFFFu, hits, d);
+    }
+    *mostly_hits = hits * 2ull > rays ? 1u : 0u;
     return ((unsigned long long)hi << 32) | lo;
 }
 
@@ -953,20 +978,29 @@ __device__ __forceinline__ void stamp(const FrameParams& p, uint32_t k)
  *         for bounce rays and origin-relative for primary rays. */
 template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, unsigned char* smem,
-                                                         uint64_t* bar)
+                                                         uint64_t* bar,
+                                                         const uint32_t* ordered_bounce = nullptr)
 {
     SceneViewT<kSmem> sc;
     if constexpr (kSmem)
     {
-        stage_scene(smem, bar, p.scene, p.layout.bytes);
-        sc = make_view<true>(smem, p.layout);
-        unsigned char* extra = smem + p.layout.bytes;
-        const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
         const uint32_t n_nodes = p.layout.n_nodes;
+        /* layout of the dynamic shared memory: blob | rel_num (kRel) | node copies */
+        unsigned char* extra = smem + p.layout.bytes;
+        float* rel_num = reinterpret_cast<float*>(extra);
+        if constexpr (kRel) extra += ((size_t)p.layout.n_tris * 4u + 15u) & ~(size_t)15u;
+        float4* oct = reinterpret_cast<float4*>(extra);
+        constexpr uint32_t kB = RVPT_OCT_B_OFFSET / 16u; /* second half of every octant record */
+        const bool ordered = kOct && p.layout.off_oct != 0u;
+
+        if (ordered)
+            stage_scene(smem, bar, p.scene, p.layout.bytes, oct, oct + kB, n_nodes * 8u * 16u);
+        else
+            stage_scene(smem, bar, p.scene, p.layout.bytes);
+        sc = make_view<true>(smem, p.layout);
+        const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
         if constexpr (kRel)
         {
-            float* rel_num = reinterpret_cast<float*>(extra);
-            extra += ((size_t)p.layout.n_tris * 4u + 15u) & ~(size_t)15u;
             for (uint32_t i = threadIdx.x; i < p.layout.n_tris; i += blockDim.x)
             {
                 const float4 A = ld_f4<true>(sc.tris, 4 * i), B = ld_f4<true>(sc.tris, 4 * i + 1);
@@ -977,14 +1011,28 @@ __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, u
         if constexpr (kOct)
         {
             static_assert(kWarpsPerCta % 8 == 0, "one warp group per octant");
-            float4* oct = reinterpret_cast<float4*>(extra);
             float4* oct_rel = oct + 8 * (size_t)n_nodes;
             const uint32_t w = threadIdx.x >> 5, k = w & 7u;
             float4* dst = oct + (size_t)n_nodes * k;
             float4* dst_rel = oct_rel + (size_t)n_nodes * k;
-            constexpr uint32_t kB = RVPT_OCT_B_OFFSET / 16u; /* second half of every record */
+            /* bounce rays walk front to back only when most of them hit something (closed scenes):
+             * rays that escape gain nothing from the order and a warp's lanes, spread over the eight
+             * arrays, would then walk eight different node sequences for nothing */
+            const bool keep_ordered_abs = ordered && ordered_bounce && *ordered_bounce != 0u;
             for (uint32_t i = (w >> 3) * 32u + (threadIdx.x & 31u); i < n_nodes; i += (kWarpsPerCta / 8) * 32u)
             {
+                if (ordered)
+                {
+                    /* primary rays: the staged front-to-back arrays minus the camera origin */
+                    if constexpr (kRel)
+                    {
+                        const float4 a = dst[i], b = dst[i + kB];
+                        dst_rel[i] = make_float4(a.x - o.x, a.y - o.x, a.z - o.y, a.w - o.y);
+                        dst_rel[i + kB] = make_float4(b.x - o.z, b.y - o.z, b.z, b.w);
+                    }
+                    if (keep_ordered_abs) continue;
+                }
+                /* reference-order copy for octant k: (near, far) per axis from the plain node */
                 const float4 n0 = ld_f4<true>(sc.nodes, 2 * i), n1 = ld_f4<true>(sc.nodes, 2 * i + 1);
                 const float ax = (k & 1u) ? n0.y : n0.x, bx = (k & 1u) ? n0.x : n0.y;
                 const float ay = (k & 2u) ? n0.w : n0.z, by = (k & 2u) ? n0.z : n0.w;
@@ -993,8 +1041,11 @@ __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, u
                 dst[i + kB] = make_float4(az, bz, n1.z, n1.w);
                 if constexpr (kRel)
                 {
-                    dst_rel[i] = make_float4(ax - o.x, bx - o.x, ay - o.y, by - o.y);
-                    dst_rel[i + kB] = make_float4(az - o.z, bz - o.z, n1.z, n1.w);
+                    if (!ordered)
+                    {
+                        dst_rel[i] = make_float4(ax - o.x, bx - o.x, ay - o.y, by - o.y);
+                        dst_rel[i + kB] = make_float4(az - o.z, bz - o.z, n1.z, n1.w);
+                    }
                 }
             }
             sc.oct_nodes = smem_u32(oct);
@@ -1030,6 +1081,7 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 
     __shared__ unsigned long long small_waves;
+    __shared__ uint32_t ordered_bounce; /* bounce rays walk the front-to-back arrays this frame */
 
     stamp(p, 0);
     /* with bounce waves, the next frame's stats set is zeroed after the first grid barrier:
@@ -1037,10 +1089,15 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     clear_next_counters(p, p.max_bounces < 2);
     if (threadIdx.x < 32)
     {
-        const unsigned long long m = forecast_small_waves(p);
-        if (threadIdx.x == 0) small_waves = m;
+        uint32_t mostly_hits;
+        const unsigned long long m = forecast_small_waves(p, &mostly_hits);
+        if (threadIdx.x == 0)
+        {
+            small_waves = m;
+            ordered_bounce = mostly_hits;
+        }
     }
-    const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);
+    const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar, &ordered_bounce);
     stamp(p, 1);
 
     primary_phase<kSmem, kRel, kOct>(p, sc);

@@ -221,3 +221,92 @@ def test_obj_roundtrip_preserves_float32(rv, tmp_path):
     write_obj(tmp_path / "m.obj", v, f)
     v2, f2 = parse_obj((tmp_path / "m.obj").read_text())
     assert np.array_equal(v.view(np.uint32), v2.view(np.uint32)) and np.array_equal(f, f2)
+
+
+def _octant_layouts(rv, nodes, tris):
+    from rvpt_b200 import _lib
+    lib = _lib.load()
+    n = C.c_size_t(0)
+    assert lib.rvpt_b200_octant_layouts(nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris), None, 0,
+                                        C.byref(n)) == 0
+    out = np.zeros(n.value * 8 * 8, np.float32)
+    assert lib.rvpt_b200_octant_layouts(nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris),
+                                        out.ctypes.data, out.size, C.byref(n)) == 0
+    a = out[: n.value * 32].reshape(8, n.value, 4)
+    b = out[n.value * 32:].reshape(8, n.value, 4)
+    return a, b.copy()
+
+
+@pytest.mark.parametrize("scene_name", ["builtin", "cornell"])
+def test_front_to_back_octant_layouts(rv, scene_name):
+    """The eight per-octant node arrays the engine uploads next to a scene (engine.cu::
+    build_octant_layouts): every array is the same tree — same boxes (as near/far pairs for the
+    octant), same leaves — in its own pre-order with consistent skip links, and it puts the child
+    lying earlier along the octant's direction first."""
+    scene = rv.builtin_scene() if scene_name == "builtin" else rv.cornell_scene()
+    nodes, perm = rv.build_bvh(scene.triangles)
+    tris = np.ascontiguousarray(scene.triangles[perm])
+    A, B = _octant_layouts(rv, nodes, tris)
+    n = A.shape[1]
+    assert n == len(nodes)
+    ref_boxes = sorted(tuple(float(v) for v in nd["bounds"]) for nd in nodes)
+    n_leaves = int((nodes["primitive_count"] > 0).sum())
+    END = 0xFFFFFFFF
+    for k in range(8):
+        skip = B[k, :, 2].view(np.uint32)
+        leaf = B[k, :, 3].view(np.uint32)
+        sx, sy, sz = k & 1, (k >> 1) & 1, (k >> 2) & 1
+        lo = lambda near, far, s: np.where(s, far, near)  # noqa: E731
+        hi = lambda near, far, s: np.where(s, near, far)  # noqa: E731
+        boxes = np.stack([lo(A[k, :, 0], A[k, :, 1], sx), hi(A[k, :, 0], A[k, :, 1], sx),
+                          lo(A[k, :, 2], A[k, :, 3], sy), hi(A[k, :, 2], A[k, :, 3], sy),
+                          lo(B[k, :, 0], B[k, :, 1], sz), hi(B[k, :, 0], B[k, :, 1], sz)], 1)
+        assert sorted(tuple(float(v) for v in r) for r in boxes) == ref_boxes
+        assert int((leaf != END).sum()) == n_leaves
+        # pre-order consistency: an inner node's first child is the next record; the second child starts
+        # where the first child's subtree ends; a subtree's skip is its parent's second child or skip
+        def check(i, end):
+            assert (skip[i] == END and end == n) or skip[i] == end, (k, i)
+            if leaf[i] != END:
+                return i + 1
+            c0 = i + 1
+            c1 = int(skip[c0]) if skip[c0] != END else n
+            check(c0, c1)
+            check(c1, end)
+            # front to back along the axis where the children's centres differ most
+            ca, cb = boxes[c0].reshape(3, 2).sum(1), boxes[c1].reshape(3, 2).sum(1)
+            ax = int(np.argmax(np.abs(cb - ca)))
+            sgn = -1.0 if (k >> ax) & 1 else 1.0
+            assert (cb[ax] - ca[ax]) * sgn >= 0, (k, i)
+            return end
+        import sys
+        sys.setrecursionlimit(10000)
+        check(0, n)
+        # every leaf's triangle range appears exactly once
+        assert sorted(leaf[leaf != END].tolist()) == sorted(
+            set(leaf[leaf != END].tolist())), "leaf ranges must be distinct"
+
+
+def test_coincident_face_detection(rv):
+    """Scenes with two coplanar triangles overlapping with positive area keep the reference's BVH
+    child order (the first triangle visited wins a tie in t); everything else may be walked front
+    to back. Quad halves, neighbours in a flat region and parallel-but-offset faces do not count."""
+    from rvpt_b200 import _lib
+    lib = _lib.load()
+
+    def check(tris):
+        t = np.ascontiguousarray(tris)
+        return lib.rvpt_b200_has_coincident_faces(t.ctypes.data, len(t))
+
+    assert check(rv.builtin_scene().triangles) == 0
+    assert check(rv.cornell_scene(with_blocks=False).triangles) == 0
+    assert check(rv.cornell_scene().triangles) == 1          # block bottoms lie in the floor plane
+    tri = lambda a, b, c: rv.make_triangles(np.float32([a]), np.float32([b]), np.float32([c]), np.float32([0]))  # noqa: E731
+    base = tri((0, 0, 0), (1, 0, 0), (0, 1, 0))
+    assert check(np.concatenate([base, tri((0.2, 0.2, 0), (0.9, 0.1, 0), (0.1, 0.9, 0))])) == 1   # overlap
+    assert check(np.concatenate([base, tri((1, 0, 0), (1, 1, 0), (0, 1, 0))])) == 0               # shares an edge
+    assert check(np.concatenate([base, tri((1, 0, 0), (2, 0, 0), (1, -1, 0))])) == 0              # shares a vertex
+    assert check(np.concatenate([base, tri((0.2, 0.2, 1e-2), (0.9, 0.1, 1e-2), (0.1, 0.9, 1e-2))])) == 0  # offset plane
+    assert check(np.concatenate([base, tri((0.2, 0.2, 0), (0.1, 0.9, 0), (0.9, 0.1, 0))])) == 1   # opposite winding
+    tilted = tri((0, 0, 0), (1, 0, 1), (0, 1, 1))
+    assert check(np.concatenate([tilted, tri((0.1, 0.1, 0.2), (0.8, 0.1, 0.9), (0.1, 0.8, 0.9))])) == 1

@@ -1,11 +1,11 @@
 #!/bin/bash
 # sharded dynamic bounce waves: all tests, A/B bench (new default vs 0x40 = old static dealing), timeline
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for v in fcast nofcast; do
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|words differ|Error" | tail -12
+for v in ord ref; do
   case $v in
-    fcast) unset RVPT_B200_EXTRA_FLAGS;;
-    nofcast) export RVPT_B200_EXTRA_FLAGS=0x40;;
+    ord) unset RVPT_B200_EXTRA_FLAGS;;
+    ref) export RVPT_B200_EXTRA_FLAGS=0x80;;
   esac
   timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${v}_n1.json 2> gpurun_out/bench_${v}_n1.err
   timeout 300 python bench.py --steps 30 --warmup 3 --pose pinned --no-cpu-baseline > gpurun_out/bench_${v}_pinned.json 2>/dev/null
@@ -14,7 +14,7 @@ done
 unset RVPT_B200_EXTRA_FLAGS
 python - <<PY
 import json
-for v in ("fcast","nofcast"):
+for v in ("ord","ref"):
   for n in ('n1','pinned','cornell'):
     try:
         d=json.load(open('gpurun_out/bench_%s_%s.json'%(v,n)))
