@@ -163,12 +163,18 @@ def _box(lo, hi, material_id) -> np.ndarray:
     ])
 
 
-def cornell_scene(with_bunny: bool = True, with_blocks: bool = True) -> Scene:
+def cornell_scene(with_bunny: bool = True, with_blocks: bool = True, block_gap: float = 0.01) -> Scene:
     """BASELINE.json config 3: a Cornell box generated in code, open towards
     the camera (a closed box renders black: paths that exhaust their bounces
     return 0, integrators.glsl:674-675), an emissive ceiling patch, red / green
     / white Lambert walls, optional mirror + dielectric blocks, the bunny
-    inside. Camera: position (0, 1, -3.2) looking +z."""
+    inside. Camera: position (0, 1, -3.2) looking +z.
+
+    The blocks hover `block_gap` above the floor (as the light patch hangs 1 cm
+    below the ceiling) so that no two faces of the scene coincide; with
+    `block_gap=0` their bottom faces lie in the floor plane, every ray through
+    them ties in t, and the engine keeps the reference's BVH child order
+    (rvpt_abi.h, RVPT_B200_FLAG_REFERENCE_ORDER) — the tests use both."""
     W, R, G, LIGHT, MIRR, GLASS = 0, 1, 2, 3, 4, 5
     mats = np.concatenate([
         make_material((0.73, 0.73, 0.73, 0)),
@@ -189,8 +195,9 @@ def cornell_scene(with_bunny: bool = True, with_blocks: bool = True) -> Scene:
               (0.4, y1 - 0.01, -0.4), LIGHT),
     ]
     if with_blocks:
-        parts.append(_box((-0.95, 0.0, 0.35), (-0.35, 1.3, 0.95), MIRR))
-        parts.append(_box((0.45, 0.0, -0.65), (0.95, 0.6, -0.15), GLASS))
+        g = float(block_gap)
+        parts.append(_box((-0.95, g, 0.35), (-0.35, 1.3 + g, 0.95), MIRR))
+        parts.append(_box((0.45, g, -0.65), (0.95, 0.6 + g, -0.15), GLASS))
     if with_bunny:
         vertices, faces = builtin_mesh()
         v = vertices * np.float32(0.55) + np.asarray([0.15, 0.0, 0.1], np.float32)

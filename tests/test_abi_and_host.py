@@ -300,7 +300,8 @@ def test_coincident_face_detection(rv):
 
     assert check(rv.builtin_scene().triangles) == 0
     assert check(rv.cornell_scene(with_blocks=False).triangles) == 0
-    assert check(rv.cornell_scene().triangles) == 1          # block bottoms lie in the floor plane
+    assert check(rv.cornell_scene().triangles) == 0          # blocks hover 1 cm above the floor
+    assert check(rv.cornell_scene(block_gap=0.0).triangles) == 1   # block bottoms lie in the floor plane
     tri = lambda a, b, c: rv.make_triangles(np.float32([a]), np.float32([b]), np.float32([c]), np.float32([0]))  # noqa: E731
     base = tri((0, 0, 0), (1, 0, 0), (0, 1, 0))
     assert check(np.concatenate([base, tri((0.2, 0.2, 0), (0.9, 0.1, 0), (0.1, 0.9, 0))])) == 1   # overlap

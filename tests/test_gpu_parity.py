@@ -598,12 +598,12 @@ def test_wave_forecast_is_scheduling_only(rv, oracle_mod, builtin):
         _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"forecast flags={flags}")
 
 
-@pytest.mark.parametrize("scene_name", ["builtin", "cornell", "cornell_open"])
+@pytest.mark.parametrize("scene_name", ["builtin", "cornell", "cornell_on_floor"])
 def test_front_to_back_order_equals_reference_order(rv, oracle_mod, builtin, cornell, scene_name):
     """Scenes without coincident faces are walked front to back per direction octant — primary
     rays always, bounce rays from the second frame on when most of them hit something (the
-    closed box) — while RVPT_B200_FLAG_REFERENCE_ORDER and scenes WITH coincident faces (the
-    Cornell blocks stand on the floor with their bottom faces in its plane) use the reference's
+    closed box) — while RVPT_B200_FLAG_REFERENCE_ORDER and scenes WITH coincident faces (Cornell
+    blocks standing on the floor with their bottom faces in its plane) use the reference's
     child order (intersection.glsl:402-406). Every variant must equal the oracle, which walks the
     reference's order: the nearest accepted hit is order-independent when no two faces coincide."""
     from conftest import PreparedScene
@@ -611,10 +611,10 @@ def test_front_to_back_order_equals_reference_order(rv, oracle_mod, builtin, cor
     if scene_name == "builtin":
         prep, pose, fov, want_order = builtin, PINNED_POSE, 90.0, 1
     elif scene_name == "cornell":
-        prep, pose, fov, want_order = cornell, CORNELL_POSE, 60.0, 0
+        prep, pose, fov, want_order = cornell, CORNELL_POSE, 60.0, 1
     else:
-        prep = PreparedScene(rv, rv.cornell_scene(with_blocks=False))
-        pose, fov, want_order = CORNELL_POSE, 60.0, 1
+        prep = PreparedScene(rv, rv.cornell_scene(block_gap=0.0))  # block bottoms in the floor plane
+        pose, fov, want_order = CORNELL_POSE, 60.0, 0
     a, ora, st_a = _render_both(rv, oracle_mod, prep, 320, 192, pose, frames=4, fov=fov)
     b, _, st_b = _render_both(rv, oracle_mod, prep, 320, 192, pose, frames=4, fov=fov,
                               flags=_lib.FLAG_REFERENCE_ORDER, oracle_flags=0)
