@@ -1,5 +1,6 @@
 #!/bin/bash
-# refresh of every r01 artefact with the current kernels: profile script, bounce sweep, other workloads, timelines
+# Refresh of every per-round artefact under gpurun_out/ (then: python tools/summarize_profile.py r01; cp gpurun_out/r01_timeline_*.md profiles/):
+# tests + bench + ncu launch list + ncu full capture + sanitizer (gpu_profile.sh), bounce sweep, the other workloads, timelines.
 bash tools/gpu_profile.sh r01
 timeout 600 python tools/bounce_sweep.py r01 > gpurun_out/sweep.log 2>&1; cp profiles/r01_bounce_sweep.md gpurun_out/ 2>/dev/null; tail -2 gpurun_out/sweep.log
 timeout 300 python bench.py --steps 10 --warmup 3 --scene cornell --no-cpu-baseline > gpurun_out/bench_r01_cornell.json 2>/dev/null
