@@ -110,7 +110,7 @@ struct WaveCounters
     /* primary phase work distribution: one counter per shard, 128 B apart so the
      * shards live in different L2 atomic units; shard k hands out chunks k, k+16, ... */
     uint32_t chunk_ctr[RVPT_CHUNK_SHARDS * 32u];
-    uint32_t work_ctr[64]; /* bounce phase work distribution, per bounce (static + claimed eighth) */
+    uint32_t work_ctr[64]; /* k_bounce (one launch per wave): the claimed eighth of wave b */
     /* k_frame's big bounce waves: sharded like chunk_ctr, wave b uses set b & 1 */
     uint32_t bounce_ctr[2][RVPT_CHUNK_SHARDS * 32u];
     uint32_t qcount[64];   /* survivors pushed by bounce b (read by b+1) */

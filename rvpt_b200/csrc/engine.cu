@@ -798,7 +798,7 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
     if (rc) return rc;
     /* front-to-back walking needs an order-independent nearest hit; only small scenes can use it */
     if (!(ctx->flags & (RVPT_B200_FLAG_REFERENCE_ORDER | RVPT_B200_FLAG_NO_OCTANTS | RVPT_B200_FLAG_BRUTE_FORCE)) &&
-        n_triangles <= 4096)
+        n_triangles <= 512) /* more triangles never fit the octant arrays (<= 400 nodes) */
         ps.coincident_faces = has_coincident_faces(triangles, n_triangles);
     else
         ps.coincident_faces = true;

@@ -2,12 +2,19 @@
  * kernels.cu — the sm_100a wavefront path-tracing kernels.
  *
  * Replaces the reference's per-pixel megakernel (assets/shaders/compute_pass.comp
- * ::main and everything it includes) with
+ * ::main and everything it includes) with two phases
  *
- *   k_primary   ray generation + bounce 0, fused (camera.glsl:29-99,
+ *   primary     ray generation + bounce 0, fused (camera.glsl:29-99,
  *               compute_pass.comp:121-167, integrators.glsl:547-677 iteration 0)
- *   k_bounce    one launch per later bounce over the compacted path queue
+ *   bounce b    one wave per later bounce over the compacted path queue
  *               (integrators.glsl:574-671 iteration b)
+ *
+ * run by  k_frame              all waves of a frame in one persistent cooperative launch
+ *                              (grid barriers between waves) — the default;
+ *         k_primary / k_bounce one launch per wave (RVPT_B200_FLAG_UNFUSED);
+ *         k_flow               no barriers at all, one ring queue per SM (RVPT_B200_FLAG_FLOW,
+ *                              experimental);
+ *         k_modes              the reference's other integrators, one thread per pixel.
  *
  * Paths that terminate do the temporal accumulation in place
  * (compute_pass.comp:146-148,161-166); survivors are compacted with a warp
@@ -857,15 +864,18 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
 /* Iteration b >= 1 of the bounce loop over queue[(b-1)&1] -> queue[b&1].
  *
  * How the wave's rays are dealt to warps depends on its size (all warp-uniform):
- *   dynamic   big waves: full 32-ray groups, mostly dealt statically, the last
- *             eighth claimed from an atomic counter;
+ *   sharded   big waves in k_frame: full 32-ray groups, every one claimed from the
+ *             sharded counters (same scheme as the primary wave);
+ *   (neither) the one-launch-per-wave kernel k_bounce: 7/8 of each warp's share is
+ *             dealt statically, the last eighth claimed from one atomic counter;
  *   spread    waves that cannot fill the machine twice over: every warp takes
  *             the same share, L = ceil(count / n_warps) <= 32 lanes at a time,
  *             so a small incoherent wave costs one short batch per warp instead
  *             of a few warps grinding through 32-wide divergent batches;
- *   in_thread (with spread, L <= 2) the paths run to their end inside their
- *             threads instead of going back through the queue; rays of the
- *             later bounces are counted as they are traced.
+ *   kInThread the paths run to their end inside their threads instead of going
+ *             back through the queue (the tail wave, and a wave whose successor
+ *             is forecast to be a tail); rays of the later bounces are counted
+ *             as they are traced.
  */
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_SHARDED 4u /* big wave, every 32-ray group claimed from the sharded counters */
@@ -885,9 +895,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    /* spread: L lanes per warp and round; otherwise full 32-ray groups, 7/8 of
-     * each warp's share dealt statically and the rest claimed from the counter
-     * (same reasoning as in primary_phase) */
+    /* spread: L lanes per warp and round; otherwise full 32-ray groups */
     const uint32_t L = spread ? min(32u, (count + n_warps - 1) / n_warps) : 32u;
     const uint32_t groups = (count + L - 1) / L;
     const uint32_t per_warp = groups / n_warps;
