@@ -22,6 +22,7 @@ FLAG_NO_OCTANTS = 0x10
 FLAG_FLOW = 0x20
 FLAG_NO_FORECAST = 0x40
 FLAG_REFERENCE_ORDER = 0x80
+FLAG_NO_QUEUE_SORT = 0x100
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 

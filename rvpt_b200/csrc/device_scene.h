@@ -13,6 +13,7 @@
 #define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
+#define RVPT_QUEUE_OCTANTS 8u      /* sub-queues of a path queue: one per direction octant */
 #define RVPT_FLOW_RING 4096u        /* k_flow: path records in one CTA's ring queue */
 /* octant node copies in shared memory: byte distance between the two float4 halves of a record */
 #define RVPT_OCT_B_OFFSET (100u * 1024u)
@@ -98,6 +99,15 @@ struct PathQueue
     float4* q3;
 };
 
+/* Per wave, in shared memory: how the wave's groups of L rays map to the eight sub-queues.
+ * pre[o] = first group of octant o, pre[8] = number of groups, cnt[o] = rays in sub-queue o. */
+struct WaveGroups
+{
+    uint32_t pre[RVPT_QUEUE_OCTANTS + 1];
+    uint32_t cnt[RVPT_QUEUE_OCTANTS];
+    uint32_t L;
+};
+
 /*
  * Device counters. Two sets of each, used alternately, so no memset is ever
  * launched: the kernel of launch L zeroes the wave set of launch L+1, and the
@@ -113,7 +123,10 @@ struct WaveCounters
     uint32_t work_ctr[64]; /* k_bounce (one launch per wave): the claimed eighth of wave b */
     /* k_frame's big bounce waves: sharded like chunk_ctr, wave b uses set b & 1 */
     uint32_t bounce_ctr[2][RVPT_CHUNK_SHARDS * 32u];
-    uint32_t qcount[64];   /* survivors pushed by bounce b (read by b+1) */
+    /* survivors pushed by bounce b (read by b+1), per direction octant of the pushed ray: every
+     * queue is eight sub-queues, so the rays a warp of the next wave loads together point into
+     * the same octant (they walk the same node array, in a similar order) */
+    uint32_t qcount[64][RVPT_QUEUE_OCTANTS];
 };
 struct FrameStats
 {
@@ -169,6 +182,7 @@ struct FrameParams
     uint32_t stats_set;           /* frame sequence parity */
     uint32_t tail_threshold;      /* waves this small finish inside their threads */
     uint32_t use_forecast;        /* wave-size forecast from the previous launch is meaningful */
+    uint32_t queue_stride;        /* entries between the sub-queues of a PathQueue (0: one queue, no sorting) */
     unsigned long long* timeline; /* optional [n_ctas][RVPT_TIMELINE_SLOTS] globaltimer stamps */
 };
 

@@ -47,6 +47,7 @@ struct rvpt_b200_ctx
     int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
     int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
     int grid_frame = 0, grid_primary = 0, grid_bounce = 0, grid_flow = 0;
+    uint32_t queue_stride = 0; /* entries per octant sub-queue; 0 = unsorted single queue */
     uint32_t tail_rays_per_warp = 16; /* waves up to this many rays per resident warp finish in-thread (measured: 2..8 equal, 16 saves a barrier + wave on sparse poses) */
     uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
     uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
@@ -171,11 +172,18 @@ int ensure_frame_buffers(rvpt_b200_ctx* ctx)
         CU(cudaMalloc(&ctx->d_out_raster, (size_t)ctx->W * ctx->H * 4));
         CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
     }
+    /* Every queue is eight sub-queues (one per direction octant of the queued ray), each able to
+     * hold every path: 8 x 64 B per pixel and queue — 2.1 GB at 1080p, 8.5 GB at 4K, of 180 GB.
+     * Images beyond ~16 GiB of queues keep one unsorted queue. */
+    ctx->queue_stride = (!(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT) &&
+                         slots * 64u * 2u * RVPT_QUEUE_OCTANTS <= ((size_t)16 << 30))
+                            ? (uint32_t)slots
+                            : 0u;
     for (int i = 0; i < 2; ++i)
     {
         /* queue 0 doubles as the per-CTA rings of k_flow (at most 2 CTAs of 1024 threads per SM) */
-        const size_t entries =
-            i == 0 ? std::max(slots, (size_t)ctx->num_sms * 2u * RVPT_FLOW_RING) : slots;
+        const size_t own = ctx->queue_stride ? slots * RVPT_QUEUE_OCTANTS : slots;
+        const size_t entries = i == 0 ? std::max(own, (size_t)ctx->num_sms * 2u * RVPT_FLOW_RING) : own;
         CU(cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4)));
         CU(cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4)));
         CU(cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4)));
@@ -687,7 +695,8 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
-                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER))
+                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
+                  RVPT_B200_FLAG_NO_QUEUE_SORT))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
@@ -873,6 +882,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
     p.timeline = ctx->d_timeline;
+    p.queue_stride = ctx->queue_stride;
 
     p.stats_set = ctx->frame_seq & 1u;
     const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;

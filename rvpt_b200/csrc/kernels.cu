@@ -601,20 +601,29 @@ __device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathSta
     return false;
 }
 
-/* Warp-aggregated append of the surviving lanes to a queue. */
+/* Warp-aggregated append of the surviving lanes to a queue: the lanes are grouped by the
+ * direction octant of their new ray (match.any), each group appends to that octant's
+ * sub-queue with one atomicAdd. qcount8 = the eight counters of this wave. */
 __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQueue& q,
-                                               uint32_t* qcount, bool alive, uint32_t slot,
-                                               const PathState& s)
+                                               uint32_t* qcount8, bool alive, uint32_t slot,
+                                               const PathState& s, bool sort)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
     if (mask == 0) return;
-    uint32_t base = 0;
-    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(qcount, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
     if (alive)
     {
-        const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
+        /* unsorted frames (open scenes: rays from neighbouring pixels, whatever their direction,
+         * walk more alike than same-octant rays from all over the image) use sub-queue 0 only */
+        const uint32_t oct = sort ? (__float_as_uint(s.d.x) >> 31) | ((__float_as_uint(s.d.y) >> 31) << 1) |
+                                        ((__float_as_uint(s.d.z) >> 31) << 2)
+                                  : 0u;
+        const uint32_t peers = __match_any_sync(mask, oct);
+        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&qcount8[oct], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t i = oct * p.queue_stride + base + __popc(peers & ((1u << lane) - 1u));
         /* path state is written once and read once: streaming stores / loads (evict-first)
          * keep L2 for the accumulation image and, for large scenes, the BVH */
         __stcs(&q.q0[i], make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot)));
@@ -622,7 +631,51 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
         __stcs(&q.q2[i], make_float4(s.thr.x, s.thr.y, s.thr.z, 0.0f));
         __stcs(&q.q3[i], make_float4(s.col.x, s.col.y, s.col.z, 0.0f));
     }
-    (void)p;
+}
+
+/* A wave's eight sub-queue counters: every warp loads them (lane o holds counter o) and gets
+ * their total (warp-uniform); *mine = this lane's counter. */
+__device__ __forceinline__ uint32_t wave_count(const uint32_t* qcount8, uint32_t* mine)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = lane < RVPT_QUEUE_OCTANTS ? *reinterpret_cast<const volatile uint32_t*>(&qcount8[lane]) : 0u;
+    *mine = c;
+    uint32_t t = c;
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+    return __shfl_sync(0xFFFFFFFFu, t, 0);
+}
+
+/* Deal a wave: L rays per group (32, or fewer when the wave is spread over all warps), groups
+ * numbered octant by octant. Warp 0 writes the table from the counters it already holds
+ * (wave_count); block-wide (ends with a barrier); wg lives in shared memory and its previous
+ * readers are behind the grid barrier / kernel boundary that precedes every wave. */
+__device__ __forceinline__ void prepare_wave(WaveGroups& wg, uint32_t mine, uint32_t count, bool spread)
+{
+    if (threadIdx.x < 32u)
+    {
+        const uint32_t lane = threadIdx.x;
+        const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+        /* spread: every warp gets one group even though each octant rounds its last group up */
+        const uint32_t share = n_warps > 2u * RVPT_QUEUE_OCTANTS ? n_warps - RVPT_QUEUE_OCTANTS : n_warps;
+        const uint32_t L = spread ? max(1u, min(32u, (count + share - 1u) / share)) : 32u;
+        const uint32_t g = (mine + L - 1u) / L;
+        uint32_t incl = g; /* inclusive scan over the eight octants */
+#pragma unroll
+        for (int d = 1; d < (int)RVPT_QUEUE_OCTANTS; d <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += v;
+        }
+        if (lane < RVPT_QUEUE_OCTANTS)
+        {
+            wg.cnt[lane] = mine;
+            wg.pre[lane] = incl - g;
+        }
+        if (lane == RVPT_QUEUE_OCTANTS - 1u) wg.pre[RVPT_QUEUE_OCTANTS] = incl;
+        if (lane == 0) wg.L = L;
+    }
+    __syncthreads();
 }
 
 /* mat4 * vec4(x,y,z,w).xyz with the columns summed left to right. */
@@ -729,7 +782,7 @@ __device__ __forceinline__ unsigned long long forecast_small_waves(const FramePa
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
 template <bool kSmem, bool kRel, bool kOct>
-__device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneViewT<kSmem>& sc)
+__device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, bool sort)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const uint32_t lane = threadIdx.x & 31u;
@@ -817,7 +870,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
         }
         if (p.max_bounces > 0)
             traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
-        push_survivors(p, p.queue[0], &wc.qcount[0], alive, slot, s);
+        push_survivors(p, p.queue[0], wc.qcount[0], alive, slot, s, sort);
       }
     }
     if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
@@ -881,7 +934,7 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
 #define RVPT_WAVE_SHARDED 4u /* big wave, every 32-ray group claimed from the sharded counters */
 template <bool kSmem, bool kOct, bool kInThread>
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
-                                             uint32_t count, uint32_t mode)
+                                             const WaveGroups& wg, uint32_t mode, bool sort)
 {
     WaveCounters& wc = p.ctr->wave[p.wave_set];
     const PathQueue qin = p.queue[(b - 1) & 1];
@@ -895,9 +948,9 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    /* spread: L lanes per warp and round; otherwise full 32-ray groups */
-    const uint32_t L = spread ? min(32u, (count + n_warps - 1) / n_warps) : 32u;
-    const uint32_t groups = (count + L - 1) / L;
+    /* spread: L lanes per warp and round; otherwise full 32-ray groups (prepare_wave) */
+    const uint32_t L = wg.L;
+    const uint32_t groups = wg.pre[RVPT_QUEUE_OCTANTS];
     const uint32_t per_warp = groups / n_warps;
     const uint32_t static_rounds = spread ? (groups + n_warps - 1) / n_warps : per_warp - (per_warp >> 3);
     const uint32_t dyn_base = static_rounds * n_warps;
@@ -934,13 +987,17 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
         if (!sharded && !spread && round + 1 >= static_rounds && lane == 0)
             claim = atomicAdd(&wc.work_ctr[b], 1u);
 
-        const uint32_t i = g * L + lane;
+        /* group g -> (octant, group inside its sub-queue): the last octant whose first group is <= g */
+        uint32_t o = g >= wg.pre[4] ? 4u : 0u;
+        o += g >= wg.pre[o + 2u] ? 2u : 0u;
+        o += g >= wg.pre[o + 1u] ? 1u : 0u;
+        const uint32_t i = (g - wg.pre[o]) * L + lane;
         bool alive = false;
         PathState s;
         uint32_t slot = 0;
-        if (lane < L && i < count)
+        if (lane < L && i < wg.cnt[o])
         {
-            load_path(qin, i, s, slot);
+            load_path(qin, o * p.queue_stride + i, s, slot);
             prefetch_prev(p, slot);
             rv_f3 sample;
             for (int k = b;; ++k)
@@ -956,7 +1013,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             }
             if (!alive) finish_sample(p, slot, sample, s.rng);
         }
-        if (!in_thread) push_survivors(p, qout, &wc.qcount[b], alive, slot, s);
+        if (!in_thread) push_survivors(p, qout, wc.qcount[b], alive, slot, s, sort);
     }
 }
 
@@ -1090,6 +1147,7 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
 
     __shared__ unsigned long long small_waves;
     __shared__ uint32_t ordered_bounce; /* bounce rays walk the front-to-back arrays this frame */
+    __shared__ WaveGroups wg;
 
     stamp(p, 0);
     /* with bounce waves, the next frame's stats set is zeroed after the first grid barrier:
@@ -1106,9 +1164,13 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         }
     }
     const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar, &ordered_bounce);
+    if constexpr (!kSmem) __syncthreads(); /* the global path stages nothing: publish the forecast */
     stamp(p, 1);
 
-    primary_phase<kSmem, kRel, kOct>(p, sc);
+    /* closed scenes (most bounce rays hit something) queue their survivors by direction octant;
+     * ordered_bounce is visible to everybody since the barriers of setup_scene */
+    const bool sort = p.queue_stride != 0u && ordered_bounce != 0u;
+    primary_phase<kSmem, kRel, kOct>(p, sc, sort);
     stamp(p, 2);
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
@@ -1117,14 +1179,16 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         grid.sync(); /* wave b-1 is complete: its survivor count is final */
         if (b == 1) clear_next_stats(p);
         stamp(p, 2 * b + 1);
-        const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&wc.qcount[b - 1]);
+        uint32_t my_count;
+        const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
         if (count == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
             atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+        prepare_wave(wg, my_count, count, count <= 64u * n_warps);
         if (count <= p.tail_threshold)
         {
-            bounce_phase<kSmem, kOct, true>(p, sc, b, count, RVPT_WAVE_SPREAD);
+            bounce_phase<kSmem, kOct, true>(p, sc, b, wg, RVPT_WAVE_SPREAD, sort);
             stamp(p, 2 * b + 2);
             break;
         }
@@ -1137,11 +1201,11 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull))
         {
             /* forecast: wave b+1 would be a tail anyway — its rays finish here, in their threads */
-            bounce_phase<kSmem, kOct, true>(p, sc, b, count, deal);
+            bounce_phase<kSmem, kOct, true>(p, sc, b, wg, deal, sort);
             stamp(p, 2 * b + 2);
             break;
         }
-        bounce_phase<kSmem, kOct, false>(p, sc, b, count, deal);
+        bounce_phase<kSmem, kOct, false>(p, sc, b, wg, deal, sort);
         stamp(p, 2 * b + 2);
     }
 }
@@ -1498,7 +1562,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     }
     else
         sc = make_view<false>(p.scene, p.layout);
-    primary_phase<kSmem, false, false>(p, sc);
+    primary_phase<kSmem, false, false>(p, sc, p.queue_stride != 0u);
 }
 
 template <bool kSmem>
@@ -1508,7 +1572,9 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     __shared__ uint64_t bar;
 
     WaveCounters& wc = p.ctr->wave[p.wave_set];
-    const uint32_t count = wc.qcount[b - 1];
+    __shared__ WaveGroups wg;
+    uint32_t my_count;
+    const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
     if (count == 0) return; /* an empty wave costs nothing but the launch */
     if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
         atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
@@ -1522,7 +1588,9 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     else
         sc = make_view<false>(p.scene, p.layout);
     const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-    bounce_phase<kSmem, false, false>(p, sc, b, count, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u);
+    prepare_wave(wg, my_count, count, count <= 64u * n_warps);
+    bounce_phase<kSmem, false, false>(p, sc, b, wg, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u,
+                                      p.queue_stride != 0u);
 }
 
 /* ======================================================================== */

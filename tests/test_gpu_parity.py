@@ -623,3 +623,21 @@ def test_front_to_back_order_equals_reference_order(rv, oracle_mod, builtin, cor
     _assert_bit_equal(b.read_accum_f32(), ora.accum, "reference order vs oracle")
     for f in range(4):
         assert st_a[f][0]["active"] == st_b[f][0]["active"] == st_a[f][1]
+
+
+@pytest.mark.parametrize("unfused", [False, True])
+def test_octant_sorted_queues_are_scheduling_only(rv, oracle_mod, cornell, unfused):
+    """Survivors are queued in eight sub-queues by the direction octant of their new ray, so the
+    rays a warp loads together walk the same node array. Which warp traces a path never changes the
+    path: images and per-bounce counts equal the oracle's with and without the sorting, fused and
+    one-launch-per-wave, incl. a spread tail (small image) and aa passes."""
+    from rvpt_b200 import _lib
+    base = _lib.FLAG_UNFUSED if unfused else 0
+    for W, H, kw in ((200, 152, dict(frames=3)), (48, 40, dict(frames=2, aa=2)), (640, 360, dict(frames=2))):
+        a, ora, st_a = _render_both(rv, oracle_mod, cornell, W, H, CORNELL_POSE, fov=60.0, flags=base,
+                                    oracle_flags=0, **kw)
+        b, _, st_b = _render_both(rv, oracle_mod, cornell, W, H, CORNELL_POSE, fov=60.0,
+                                  flags=base | _lib.FLAG_NO_QUEUE_SORT, oracle_flags=0, **kw)
+        _assert_bit_equal(a.read_accum_f32(), ora.accum, f"sorted queues {W}x{H}")
+        _assert_bit_equal(b.read_accum_f32(), ora.accum, f"single queue {W}x{H}")
+        assert st_a[-1][0]["active"] == st_b[-1][0]["active"] == st_a[-1][1]
