@@ -611,19 +611,29 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
     if (mask == 0) return;
-    if (alive)
+    uint32_t i = 0;
+    if (!sort)
     {
         /* unsorted frames (open scenes: rays from neighbouring pixels, whatever their direction,
          * walk more alike than same-octant rays from all over the image) use sub-queue 0 only */
-        const uint32_t oct = sort ? (__float_as_uint(s.d.x) >> 31) | ((__float_as_uint(s.d.y) >> 31) << 1) |
-                                        ((__float_as_uint(s.d.z) >> 31) << 2)
-                                  : 0u;
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(&qcount8[0], (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+        i = base + __popc(mask & ((1u << lane) - 1u));
+    }
+    else if (alive)
+    {
+        const uint32_t oct = (__float_as_uint(s.d.x) >> 31) | ((__float_as_uint(s.d.y) >> 31) << 1) |
+                             ((__float_as_uint(s.d.z) >> 31) << 2);
         const uint32_t peers = __match_any_sync(mask, oct);
         const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(&qcount8[oct], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
-        const uint32_t i = oct * p.queue_stride + base + __popc(peers & ((1u << lane) - 1u));
+        i = oct * p.queue_stride + base + __popc(peers & ((1u << lane) - 1u));
+    }
+    if (alive)
+    {
         /* path state is written once and read once: streaming stores / loads (evict-first)
          * keep L2 for the accumulation image and, for large scenes, the BVH */
         __stcs(&q.q0[i], make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot)));
