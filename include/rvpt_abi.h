@@ -96,14 +96,17 @@ typedef struct rvpt_material
 
 #define RVPT_MAX_BOUNCE_STATS 64
 
-/* Counters of the last completed frame (all `aa` passes summed). */
+/* Counters of the last render_frame call (all `aa` passes summed) or, after a batched
+ * rvpt_b200_render_frames, of its last launch: `frames` frames summed. */
 typedef struct rvpt_b200_stats
 {
-    uint64_t samples;                              /* pixels x aa rendered by this ctx */
+    uint64_t samples;                              /* pixels x aa x frames rendered by this ctx */
     uint64_t segments;                             /* intersect_scene calls = sum of active[] */
     uint64_t active[RVPT_MAX_BOUNCE_STATS];        /* rays traced at bounce b */
     uint32_t kernel_launches;                      /* kernels launched for the frame */
     uint32_t traversal_order;                      /* 0 reference child order, 1 front to back (see REFERENCE_ORDER) */
+    uint32_t frames;                               /* frames the counters cover (1 unless batched) */
+    uint32_t reserved;
 } rvpt_b200_stats;
 
 /* ------------------------------------------------------------------------ */
@@ -139,10 +142,10 @@ typedef struct rvpt_b200_stats
  * test then uses the reference's per-axis min/max form for every ray). Same
  * results; for A/B measurements. */
 #define RVPT_B200_FLAG_NO_OCTANTS 0x10u
-/* Render the frame with the barrier-free kernel (k_flow): every SM streams its
- * own wavefront queue instead of the whole grid synchronising between bounce
- * waves. Same results. */
-#define RVPT_B200_FLAG_FLOW 0x20u
+/* rvpt_b200_render_frames launches every frame on its own instead of merging the waves of
+ * consecutive frames into batched launches. Same results; for A/B measurements. (0x20 was
+ * the experimental barrier-free kernel of ABI version 1.) */
+#define RVPT_B200_FLAG_NO_BATCH 0x200u
 /* Do not use the previous frame's per-bounce ray counts to forecast tiny waves (k_frame
  * then always queues survivors and pays the barrier + tail wave behind them). Same
  * results; for A/B measurements. */
@@ -202,10 +205,13 @@ RVPT_API int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nod
 /* ------------------------------------------------------------------------ */
 RVPT_API int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* settings,
                                     const float camera[20]);
-/* A progressive batch: n_frames consecutive render_frame calls with
- * current_frame, current_frame+1, ... (the counter rule of rvpt.cpp:102-111
- * when nothing changes), submitted back to back: one kernel launch per frame,
- * no host synchronisation in between. Stats are those of the last frame. */
+/* A progressive batch: the result of n_frames consecutive render_frame calls with
+ * current_frame, current_frame+1, ... (the counter rule of rvpt.cpp:102-111 when nothing
+ * changes), bit for bit — but only the images after the LAST frame are observable, which lets
+ * the engine merge the frames' waves: with aa == 1 and integrator 9 everywhere, as many frames
+ * as the path-queue budget allows (<= 64) share ONE kernel launch (scene staged once, one set
+ * of grid barriers, samples folded into the running mean in frame order at the end).
+ * No host synchronisation. Stats are those of the last launch (stats.frames frames). */
 RVPT_API int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_settings* settings,
                                      const float camera[20], uint32_t n_frames);
 RVPT_API int rvpt_b200_sync(rvpt_b200_ctx* ctx);

@@ -19,10 +19,10 @@ FLAG_REFERENCE_DISPATCH = 0x2
 FLAG_BRUTE_FORCE = 0x4
 FLAG_UNFUSED = 0x8
 FLAG_NO_OCTANTS = 0x10
-FLAG_FLOW = 0x20
 FLAG_NO_FORECAST = 0x40
 FLAG_REFERENCE_ORDER = 0x80
 FLAG_NO_QUEUE_SORT = 0x100
+FLAG_NO_BATCH = 0x200
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -34,6 +34,8 @@ class Stats(C.Structure):
         ("active", C.c_uint64 * MAX_BOUNCE_STATS),
         ("kernel_launches", C.c_uint32),
         ("traversal_order", C.c_uint32),
+        ("frames", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -14,7 +14,10 @@
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
 #define RVPT_QUEUE_OCTANTS 8u      /* sub-queues of a path queue: one per direction octant */
-#define RVPT_FLOW_RING 4096u        /* k_flow: path records in one CTA's ring queue */
+/* batched launches (render_frames): a queued path carries `slot | frame_in_batch << 26` */
+#define RVPT_BATCH_SLOT_BITS 26u
+#define RVPT_BATCH_SLOT_MASK ((1u << RVPT_BATCH_SLOT_BITS) - 1u)
+#define RVPT_MAX_BATCH 64u          /* frames per launch (6 tag bits) */
 /* octant node copies in shared memory: byte distance between the two float4 halves of a record */
 #define RVPT_OCT_B_OFFSET (100u * 1024u)
 #define RVPT_TIMELINE_SLOTS 16u     /* per-CTA phase stamps of the last frame kernel */
@@ -109,10 +112,12 @@ struct WaveGroups
 };
 
 /*
- * Device counters. Two sets of each, used alternately, so no memset is ever
- * launched: the kernel of launch L zeroes the wave set of launch L+1, and the
- * first pass of frame F zeroes the stats set of frame F+1 (whose previous user,
- * launch L-1 / frame F-1, has completed in stream order).
+ * Device counters. Nothing here depends on host-side launch parity, so a CUDA graph that
+ * captured any number of launches replays correctly: the LAST CTA to leave a launch
+ * (done_ctas) re-zeroes the wave counters for the next launch and, when the launch completes
+ * a frame (or a batch of frames), publishes the per-bounce ray counts into `last` and zeroes
+ * `stats`. `last` is what the host reads (rvpt_b200_get_stats) and what the next launch's
+ * wave-size forecast looks at.
  */
 #define RVPT_CHUNK_SHARDS 16u
 struct WaveCounters
@@ -130,12 +135,15 @@ struct WaveCounters
 };
 struct FrameStats
 {
-    unsigned long long active[64]; /* rays traced at bounce b, whole frame (all aa passes) */
+    unsigned long long active[64]; /* rays traced at bounce b */
 };
 struct FrameCounters
 {
-    WaveCounters wave[2];
-    FrameStats stats[2];
+    WaveCounters wave;   /* all zero between launches */
+    FrameStats stats;    /* the frame (all aa passes) or batch in flight; zero between frames */
+    FrameStats last;     /* the last completed frame / batch */
+    uint32_t last_sets;  /* full-image sample sets `last` covers: aa, or the frames of a batch */
+    uint32_t done_ctas;  /* CTAs that have left the current launch */
 };
 
 /* Per-frame constants, passed by value as a kernel parameter. */
@@ -178,8 +186,15 @@ struct FrameParams
     uchar4* out_raster;           /* rgba8 result, raster (nranks == 1) */
     float4* carry;                /* per-slot (sum.xyz, rng) between aa passes */
     FrameCounters* ctr;
-    uint32_t wave_set;            /* launch sequence parity */
-    uint32_t stats_set;           /* frame sequence parity */
+    uint32_t last_of_pass;        /* this launch is the last one that uses the wave counters (fused: always) */
+    uint32_t last_of_frame;       /* ... and the last one of the frame / batch: publish the stats */
+    /* batched launch (rvpt_b200_render_frames): frames frame .. frame + n_batch - 1 in one launch.
+     * Samples are not folded into the running mean as they finish — frames of one pixel must be
+     * folded in order — but parked in samples[frame_in_batch * sample_stride + slot]; the resolve
+     * phase at the end of the launch folds them in frame order (compute_pass.comp:161-163). */
+    uint32_t n_batch;             /* 0 = classic single-frame launch */
+    uint32_t sample_stride;       /* slots per frame in `samples` */
+    float4* samples;
     uint32_t tail_threshold;      /* waves this small finish inside their threads */
     uint32_t use_forecast;        /* wave-size forecast from the previous launch is meaningful */
     uint32_t queue_stride;        /* entries between the sub-queues of a PathQueue (0: one queue, no sorting) */

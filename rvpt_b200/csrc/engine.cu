@@ -32,7 +32,7 @@ static_assert(sizeof(rvpt_material) == 48, "Material must stay 48 bytes");
 static_assert(sizeof(DevNode) == 32 && sizeof(DevTri) == 64 && sizeof(DevMaterial) == 48,
               "device records are 2/4/3 float4");
 
-#define RVPT_ABI_VERSION 1u
+#define RVPT_ABI_VERSION 2u
 /* scenes whose blob fits this budget are staged into shared memory per CTA */
 #define RVPT_SMEM_SCENE_LIMIT (224u * 1024u) /* one 1024-thread CTA per SM owns the SM's shared memory (227 KB opt-in max) */
 
@@ -46,11 +46,13 @@ struct rvpt_b200_ctx
     int num_sms = 0;
     int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
     int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
-    int grid_frame = 0, grid_primary = 0, grid_bounce = 0, grid_flow = 0;
+    int grid_frame = 0, grid_primary = 0, grid_bounce = 0;
     uint32_t queue_stride = 0; /* entries per octant sub-queue; 0 = unsorted single queue */
+    bool queue_sorted = false; /* the queues are eight octant sub-queues */
+    uint32_t batch_cap = 0;    /* frames per launch the queues and the sample buffer hold (>= 1 once allocated) */
+    size_t queue_budget = (size_t)64 << 30; /* bytes the path queues may take (of 180 GB) */
     uint32_t tail_rays_per_warp = 16; /* waves up to this many rays per resident warp finish in-thread (measured: 2..8 equal, 16 saves a barrier + wave on sparse poses) */
-    uint32_t launch_seq = 0; /* parity selects the WaveCounters set */
-    uint32_t frame_seq = 0;  /* parity selects the FrameStats set */
+    uint32_t frame_seq = 0;  /* frames / batches launched so far (the forecast needs one behind it) */
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -73,6 +75,7 @@ struct rvpt_b200_ctx
     uchar4* d_out_raster = nullptr; /* nranks == 1, or exported by the display rank */
     uchar4* peer_out_raster = nullptr; /* display rank's image, mapped through CUDA IPC */
     float4* d_carry = nullptr;      /* allocated on first aa > 1 */
+    float4* d_samples = nullptr;    /* batched launches: [batch_cap][slots] parked samples */
     PathQueue queue[2]{};
     FrameCounters* d_ctr = nullptr;
     void* d_scratch = nullptr; /* raster-sized float4 staging for read-backs */
@@ -81,7 +84,7 @@ struct rvpt_b200_ctx
     int last_max_bounces = 0;
     int last_aa = 0;
     uint32_t last_launches = 0;
-    uint32_t last_stats_set = 0;
+    uint32_t last_frames = 0; /* frames the last launch covered (stats) */
 
     /* per-CTA phase stamps of the last frame kernel (set_timeline) */
     unsigned long long* d_timeline = nullptr;
@@ -131,14 +134,8 @@ size_t accum_elem_bytes(const rvpt_b200_ctx* ctx)
     return (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? 4u : 16u;
 }
 
-void free_frame_buffers(rvpt_b200_ctx* ctx)
+void free_queues(rvpt_b200_ctx* ctx)
 {
-    cudaFree(ctx->d_accum);
-    cudaFree(ctx->d_out_tiles);
-    cudaFree(ctx->d_out_raster);
-    cudaFree(ctx->d_carry);
-    cudaFree(ctx->d_ctr);
-    cudaFree(ctx->d_scratch);
     for (int i = 0; i < 2; ++i)
     {
         cudaFree(ctx->queue[i].q0);
@@ -147,6 +144,20 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
         cudaFree(ctx->queue[i].q3);
         ctx->queue[i] = PathQueue{};
     }
+    cudaFree(ctx->d_samples);
+    ctx->d_samples = nullptr;
+    ctx->batch_cap = 0;
+}
+
+void free_frame_buffers(rvpt_b200_ctx* ctx)
+{
+    cudaFree(ctx->d_accum);
+    cudaFree(ctx->d_out_tiles);
+    cudaFree(ctx->d_out_raster);
+    cudaFree(ctx->d_carry);
+    cudaFree(ctx->d_ctr);
+    cudaFree(ctx->d_scratch);
+    free_queues(ctx);
     ctx->d_accum = ctx->d_out_tiles = nullptr;
     ctx->accum = ctx->out_tiles = nullptr;
     ctx->d_out_raster = nullptr;
@@ -154,6 +165,49 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
     ctx->d_ctr = nullptr;
     ctx->d_scratch = nullptr;
     ctx->buffers_ready = false;
+}
+
+/* Frames one launch may cover with the path queues inside their memory budget (every queue is
+ * eight octant sub-queues, each able to hold every path of the launch: 8 x 64 B per pixel,
+ * frame and queue — 2.1 GB per 1080p frame of a batch, 8.5 GB per 4K frame). */
+uint32_t max_batch(const rvpt_b200_ctx* ctx)
+{
+    const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    if (slots == 0 || slots > RVPT_BATCH_SLOT_MASK) return 1;
+    const bool sorted = !(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT);
+    const size_t per_frame = slots * 64u * 2u * (sorted ? RVPT_QUEUE_OCTANTS : 1u);
+    size_t cap = ctx->queue_budget / per_frame;
+    cap = std::min<size_t>(cap, RVPT_MAX_BATCH);
+    cap = std::min<size_t>(cap, ((size_t)1 << 31) / slots); /* queue indices are 32-bit */
+    return (uint32_t)std::max<size_t>(cap, 1);
+}
+
+/* (Re)allocates the path queues and the parked-sample buffer for launches of up to `frames`
+ * frames. Queues: eight sub-queues (one per direction octant of the queued ray) of
+ * slots * batch_cap entries each while that fits the budget, else one unsorted queue. */
+int ensure_batch_capacity(rvpt_b200_ctx* ctx, uint32_t frames)
+{
+    if (frames <= ctx->batch_cap) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_queues(ctx);
+    const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
+    const size_t per_queue = slots * frames; /* paths of one launch */
+    ctx->queue_sorted = !(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT) &&
+                        per_queue * 64u * 2u * RVPT_QUEUE_OCTANTS <= std::max(ctx->queue_budget, (size_t)16 << 30) &&
+                        per_queue * RVPT_QUEUE_OCTANTS < ((size_t)1 << 32);
+    ctx->queue_stride = ctx->queue_sorted ? (uint32_t)per_queue : 0u;
+    const size_t entries = std::max<size_t>(ctx->queue_sorted ? per_queue * RVPT_QUEUE_OCTANTS : per_queue, 1);
+    for (int i = 0; i < 2; ++i)
+    {
+        CU(cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4)));
+        CU(cudaMalloc(&ctx->queue[i].q3, entries * sizeof(float4)));
+    }
+    if (frames > 1) CU(cudaMalloc(&ctx->d_samples, std::max<size_t>(per_queue, 1) * sizeof(float4)));
+    ctx->batch_cap = frames;
+    return 0;
 }
 
 int ensure_frame_buffers(rvpt_b200_ctx* ctx)
@@ -172,27 +226,10 @@ int ensure_frame_buffers(rvpt_b200_ctx* ctx)
         CU(cudaMalloc(&ctx->d_out_raster, (size_t)ctx->W * ctx->H * 4));
         CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
     }
-    /* Every queue is eight sub-queues (one per direction octant of the queued ray), each able to
-     * hold every path: 8 x 64 B per pixel and queue — 2.1 GB at 1080p, 8.5 GB at 4K, of 180 GB.
-     * Images beyond ~16 GiB of queues keep one unsorted queue. */
-    ctx->queue_stride = (!(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT) &&
-                         slots * 64u * 2u * RVPT_QUEUE_OCTANTS <= ((size_t)16 << 30))
-                            ? (uint32_t)slots
-                            : 0u;
-    for (int i = 0; i < 2; ++i)
-    {
-        /* queue 0 doubles as the per-CTA rings of k_flow (at most 2 CTAs of 1024 threads per SM) */
-        const size_t own = ctx->queue_stride ? slots * RVPT_QUEUE_OCTANTS : slots;
-        const size_t entries = i == 0 ? std::max(own, (size_t)ctx->num_sms * 2u * RVPT_FLOW_RING) : own;
-        CU(cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q3, entries * sizeof(float4)));
-    }
     CU(cudaMalloc(&ctx->d_ctr, sizeof(FrameCounters)));
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(FrameCounters), ctx->stream));
     ctx->buffers_ready = true;
-    return 0;
+    return ensure_batch_capacity(ctx, 1);
 }
 
 int ensure_scratch(rvpt_b200_ctx* ctx)
@@ -648,16 +685,25 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
         if (ctx->scene_smem) CU(rvpt::configure_kernels(RVPT_SMEM_SCENE_LIMIT));
         CU(rvpt::occupancy(&occ_f, &occ_p, &occ_b, ctx->scene_smem, ctx->scene_oct, L.bytes, L.n_nodes,
                            L.n_tris));
-        int occ_w = 0;
-        CU(rvpt::flow_occupancy(&occ_w, ctx->scene_smem, ctx->scene_oct, L.bytes, L.n_nodes, L.n_tris));
-        if (occ_f < 1 || occ_p < 1 || occ_b < 1 || occ_w < 1)
-            return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d/%d)",
-                        occ_f, occ_p, occ_b, occ_w);
-        ctx->grid_flow = ctx->num_sms * std::min(occ_w, 2);
+        if (occ_f < 1 || occ_p < 1 || occ_b < 1)
+            return fail(ctx, RVPT_B200_ECUDA, "kernels do not fit on an SM (occupancy %d/%d/%d)",
+                        occ_f, occ_p, occ_b);
         /* persistent grids: every CTA is resident (a requirement of the cooperative launch) */
         ctx->grid_frame = ctx->num_sms * occ_f;
         ctx->grid_primary = ctx->num_sms * occ_p;
         ctx->grid_bounce = ctx->num_sms * occ_b;
+        /* the per-CTA timeline buffer was sized for the previous grid */
+        if (ctx->d_timeline && ctx->grid_frame > ctx->timeline_ctas)
+        {
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_timeline);
+            ctx->d_timeline = nullptr;
+            ctx->timeline_ctas = 0;
+            const size_t bytes = (size_t)ctx->grid_frame * RVPT_TIMELINE_SLOTS * sizeof(unsigned long long);
+            CU(cudaMalloc(&ctx->d_timeline, bytes));
+            CU(cudaMemset(ctx->d_timeline, 0, bytes));
+            ctx->timeline_ctas = ctx->grid_frame;
+        }
     }
     ctx->have_scene = true;
     apply_scene_l2_policy(ctx);
@@ -695,11 +741,13 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
         return fail(ctx, RVPT_B200_EINVAL, "bad image size %ux%u", width, height);
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
-                  RVPT_B200_FLAG_FLOW | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
+                  RVPT_B200_FLAG_NO_BATCH | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
                   RVPT_B200_FLAG_NO_QUEUE_SORT))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
+        ctx->queue_budget = (size_t)std::max(1, std::atoi(e)) << 20;
     ctx->device = device;
     ctx->W = width;
     ctx->H = height;
@@ -814,29 +862,21 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
     return upload_packed(ctx, ps);
 }
 
-extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs,
-                                      const float camera[20])
+namespace
 {
-    if (!ctx) return RVPT_B200_EINVAL;
-    if (!rs || !camera) return fail(ctx, RVPT_B200_EINVAL, "null settings/camera");
-    if (!ctx->have_scene) return fail(ctx, RVPT_B200_ENOSCENE, "render_frame before upload_scene");
-    if (rs->aa < 1) return fail(ctx, RVPT_B200_EINVAL, "aa = %d (reference divides by it)", rs->aa);
-    if (rs->max_bounces < 0 || rs->max_bounces > 64)
-        return fail(ctx, RVPT_B200_EINVAL, "max_bounces = %d outside [0,64]", rs->max_bounces);
+
+/* One frame (n_batch == 0: every aa pass, plus the other integrators' pixels) or one batched
+ * launch covering frames current_frame .. current_frame + n_batch - 1 (aa == 1, Kajiya only). */
+int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const float camera[20],
+                    uint32_t n_batch)
+{
     const int modes[4] = {rs->top_left_render_mode, rs->top_right_render_mode,
                           rs->bottom_left_render_mode, rs->bottom_right_render_mode};
     bool all_kajiya = true;
-    for (int m : modes)
-    {
-        /* eval_integrator's default case is integrator_Hart, the sphere-tracing heat map of
-         * distance_functions.glsl (compute_pass.comp:96-97) — outside the hot-path scope */
-        if (m < 0 || m > 9)
-            return fail(ctx, RVPT_B200_EUNSUPPORTED,
-                        "render mode %d (integrator_Hart sphere tracer) is not built; modes 0-9 are", m);
-        all_kajiya = all_kajiya && m == 9;
-    }
+    for (int m : modes) all_kajiya = all_kajiya && m == 9;
     int rc = ensure_frame_buffers(ctx);
     if (rc) return rc;
+    if ((rc = ensure_batch_capacity(ctx, std::max(n_batch, 1u)))) return rc;
     CU(cudaSetDevice(ctx->device));
     if (rs->aa > 1 && !ctx->d_carry)
         CU(cudaMalloc(&ctx->d_carry,
@@ -883,10 +923,12 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     p.ctr = ctx->d_ctr;
     p.timeline = ctx->d_timeline;
     p.queue_stride = ctx->queue_stride;
+    p.n_batch = n_batch;
+    p.samples = ctx->d_samples;
+    p.sample_stride = ctx->n_local_padded * RVPT_TILE_PIXELS;
 
-    p.stats_set = ctx->frame_seq & 1u;
     const bool unfused = (ctx->flags & RVPT_B200_FLAG_UNFUSED) != 0;
-    /* a wave with at most two rays per resident warp runs to completion in its threads */
+    /* a wave with at most this many rays per resident warp runs to completion in its threads */
     p.tail_threshold = unfused ? 0u : (uint32_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32) * ctx->tail_rays_per_warp;
     /* the previous frame's per-bounce counts forecast this frame's small waves (k_frame) */
     p.use_forecast = (!unfused && ctx->frame_seq > 0 && !(ctx->flags & RVPT_B200_FLAG_NO_FORECAST)) ? 1u : 0u;
@@ -895,14 +937,9 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     for (int pass = 0; pass < rs->aa && p.n_chunks > 0; ++pass)
     {
         p.pass = pass;
-        p.wave_set = ctx->launch_seq & 1u;
-        if (ctx->flags & RVPT_B200_FLAG_FLOW)
-        {
-            ScopedTimer tm(ctx, 0);
-            CU(rvpt::launch_flow(p, ctx->scene_smem, ctx->scene_oct, ctx->grid_flow, ctx->stream));
-            ++launches;
-        }
-        else if (!unfused)
+        p.last_of_pass = 1u;
+        p.last_of_frame = pass == rs->aa - 1 ? 1u : 0u;
+        if (!unfused)
         {
             ScopedTimer tm(ctx, 0);
             CU(rvpt::launch_frame(p, ctx->scene_smem, ctx->scene_oct, ctx->grid_frame, ctx->stream));
@@ -910,19 +947,23 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
         }
         else
         {
+            const uint32_t frame_done = p.last_of_frame;
             {
                 ScopedTimer tm(ctx, 0);
+                p.last_of_pass = rs->max_bounces < 2 ? 1u : 0u; /* the last wave's launch closes the pass */
+                p.last_of_frame = p.last_of_pass ? frame_done : 0u;
                 CU(rvpt::launch_primary(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
             }
             ++launches;
             for (int b = 1; b < rs->max_bounces; ++b)
             {
                 ScopedTimer tm(ctx, 1);
+                p.last_of_pass = b == rs->max_bounces - 1 ? 1u : 0u;
+                p.last_of_frame = p.last_of_pass ? frame_done : 0u;
                 CU(rvpt::launch_bounce(p, b, ctx->scene_smem, ctx->grid_bounce, ctx->stream));
                 ++launches;
             }
         }
-        ctx->launch_seq++;
     }
     if (!all_kajiya && p.n_chunks > 0)
     {
@@ -932,26 +973,79 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
         CU(rvpt::launch_modes(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
         ++launches;
     }
-    ctx->last_stats_set = p.stats_set;
     ctx->frame_seq++;
     ctx->frame_rendered = true;
     ctx->last_max_bounces = rs->max_bounces;
     ctx->last_aa = rs->aa;
     ctx->last_launches = launches;
+    ctx->last_frames = std::max(n_batch, 1u);
     return 0;
+}
+
+int validate_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const float camera[20])
+{
+    if (!rs || !camera) return fail(ctx, RVPT_B200_EINVAL, "null settings/camera");
+    if (!ctx->have_scene) return fail(ctx, RVPT_B200_ENOSCENE, "render_frame before upload_scene");
+    if (rs->aa < 1) return fail(ctx, RVPT_B200_EINVAL, "aa = %d (reference divides by it)", rs->aa);
+    if (rs->max_bounces < 0 || rs->max_bounces > 64)
+        return fail(ctx, RVPT_B200_EINVAL, "max_bounces = %d outside [0,64]", rs->max_bounces);
+    const int modes[4] = {rs->top_left_render_mode, rs->top_right_render_mode,
+                          rs->bottom_left_render_mode, rs->bottom_right_render_mode};
+    for (int m : modes)
+    {
+        /* eval_integrator's default case is integrator_Hart, the sphere-tracing heat map of
+         * distance_functions.glsl (compute_pass.comp:96-97) — outside the hot-path scope */
+        if (m < 0 || m > 9)
+            return fail(ctx, RVPT_B200_EUNSUPPORTED,
+                        "render mode %d (integrator_Hart sphere tracer) is not built; modes 0-9 are", m);
+    }
+    return 0;
+}
+
+} /* namespace */
+
+extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs,
+                                      const float camera[20])
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    const int rc = validate_frame(ctx, rs, camera);
+    if (rc) return rc;
+    return render_launches(ctx, rs, camera, 0);
 }
 
 extern "C" int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs,
                                        const float camera[20], uint32_t n_frames)
 {
     if (!ctx) return RVPT_B200_EINVAL;
-    if (!rs) return fail(ctx, RVPT_B200_EINVAL, "null settings");
+    int rc = validate_frame(ctx, rs, camera);
+    if (rc) return rc;
     rvpt_render_settings s = *rs;
-    for (uint32_t i = 0; i < n_frames; ++i)
+    const bool kajiya = s.top_left_render_mode == 9 && s.top_right_render_mode == 9 &&
+                        s.bottom_left_render_mode == 9 && s.bottom_right_render_mode == 9;
+    /* Batched launches: the frames' waves are merged (kernels.cu, k_frame<.., kBatch>). Needs
+     * one sample per pixel and frame (the RNG stream of a pixel runs on from sample to sample
+     * inside a frame: aa > 1 is sequential) and the wavefront integrator on every pixel. */
+    const uint32_t cap = max_batch(ctx);
+    const bool batched = n_frames > 1 && s.aa == 1 && kajiya && cap > 1 &&
+                         !(ctx->flags & (RVPT_B200_FLAG_NO_BATCH | RVPT_B200_FLAG_UNFUSED));
+    if (!batched)
     {
-        const int rc = rvpt_b200_render_frame(ctx, &s, camera);
-        if (rc) return rc;
-        s.current_frame++;
+        for (uint32_t i = 0; i < n_frames; ++i)
+        {
+            if ((rc = render_launches(ctx, &s, camera, 0))) return rc;
+            s.current_frame++;
+        }
+        return 0;
+    }
+    /* as few launches as the queue budget allows, of equal size */
+    const uint32_t n_launches = (n_frames + cap - 1) / cap;
+    const uint32_t per = (n_frames + n_launches - 1) / n_launches;
+    for (uint32_t done = 0; done < n_frames;)
+    {
+        const uint32_t n = std::min(per, n_frames - done);
+        if ((rc = render_launches(ctx, &s, camera, n))) return rc;
+        s.current_frame += n;
+        done += n;
     }
     return 0;
 }
@@ -1062,8 +1156,7 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     if (!ctx->frame_rendered) return 0;
     CU(cudaSetDevice(ctx->device));
     FrameStats h;
-    CU(cudaMemcpyAsync(&h, &ctx->d_ctr->stats[ctx->last_stats_set], sizeof(h),
-                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&h, &ctx->d_ctr->last, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < RVPT_MAX_BOUNCE_STATS; ++b)
     {
@@ -1073,6 +1166,7 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     out->samples = ctx->last_max_bounces > 0 ? h.active[0] : 0;
     out->kernel_launches = ctx->last_launches;
     out->traversal_order = ctx->layout.off_oct != 0u ? 1u : 0u;
+    out->frames = ctx->last_frames;
     return 0;
 }
 
@@ -1114,7 +1208,7 @@ extern "C" int rvpt_b200_set_timeline(rvpt_b200_ctx* ctx, int enabled)
     ctx->timeline_ctas = 0;
     if (enabled)
     {
-        const int ctas = std::max(ctx->grid_frame, ctx->grid_flow);
+        const int ctas = ctx->grid_frame;
         const size_t bytes = (size_t)ctas * RVPT_TIMELINE_SLOTS * sizeof(unsigned long long);
         CU(cudaMalloc(&ctx->d_timeline, bytes));
         CU(cudaMemset(ctx->d_timeline, 0, bytes));

@@ -12,8 +12,9 @@
  * run by  k_frame              all waves of a frame in one persistent cooperative launch
  *                              (grid barriers between waves) — the default;
  *         k_primary / k_bounce one launch per wave (RVPT_B200_FLAG_UNFUSED);
- *         k_flow               no barriers at all, one ring queue per SM (RVPT_B200_FLAG_FLOW,
- *                              experimental);
+ *                              with n_batch > 0 the launch renders a whole progressive batch
+ *                              (rvpt_b200_render_frames): the waves of all its frames are merged
+ *                              and a resolve phase folds the parked samples in frame order;
  *         k_modes              the reference's other integrators, one thread per pixel.
  *
  * Paths that terminate do the temporal accumulation in place
@@ -399,6 +400,32 @@ __device__ __forceinline__ unsigned char dev_unorm8(float x)
     return (unsigned char)__float2uint_rn(__saturatef(x) * 255.0f);
 }
 
+/* compute_pass.comp:146-148, 161-163: one step of the running mean */
+__device__ __forceinline__ rv_f3 fold_sample(rv_f3 prev, rv_f3 sampled, float frame_f, float inv_frame1,
+                                             float keep)
+{
+    const rv_f3 temporal = rv_make(prev.x * keep, prev.y * keep, prev.z * keep);
+    return rv_make((temporal.x * frame_f + sampled.x) * inv_frame1,
+                   (temporal.y * frame_f + sampled.y) * inv_frame1,
+                   (temporal.z * frame_f + sampled.z) * inv_frame1);
+}
+
+__device__ __forceinline__ void store_result(const FrameParams& p, uint32_t slot, uchar4 q, uint32_t raster)
+{
+    if (p.out_raster)
+    {
+        if (raster == 0xFFFFFFFFu)
+        {
+            uint32_t x, y;
+            slot_to_xy(p, slot, x, y);
+            raster = y * p.W + x;
+        }
+        p.out_raster[raster] = q;
+    }
+    else
+        p.out_tiles[slot] = q;
+}
+
 /* `raster` = y*W + x when the caller already knows the pixel, 0xFFFFFFFF otherwise */
 __device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t slot, rv_f3 sampled,
                                                  uint32_t raster = 0xFFFFFFFFu)
@@ -415,27 +442,13 @@ __device__ __forceinline__ void accumulate_pixel(const FrameParams& p, uint32_t 
         const float4 a = p.accum_f32[slot];
         prev = rv_make(a.x, a.y, a.z);
     }
-    const rv_f3 temporal = rv_make(prev.x * p.keep, prev.y * p.keep, prev.z * p.keep);
-    const rv_f3 acc = rv_make((temporal.x * p.frame_f + sampled.x) * p.inv_frame1,
-                              (temporal.y * p.frame_f + sampled.y) * p.inv_frame1,
-                              (temporal.z * p.frame_f + sampled.z) * p.inv_frame1);
+    const rv_f3 acc = fold_sample(prev, sampled, p.frame_f, p.inv_frame1, p.keep);
     const uchar4 q = make_uchar4(dev_unorm8(acc.x), dev_unorm8(acc.y), dev_unorm8(acc.z), 0);
     if (u8)
         p.accum_u8[slot] = q;
     else
         p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
-    if (p.out_raster)
-    {
-        if (raster == 0xFFFFFFFFu)
-        {
-            uint32_t x, y;
-            slot_to_xy(p, slot, x, y);
-            raster = y * p.W + x;
-        }
-        p.out_raster[raster] = q;
-    }
-    else
-        p.out_tiles[slot] = q;
+    store_result(p, slot, q, raster);
 }
 
 
@@ -466,9 +479,21 @@ __device__ __forceinline__ void prefetch_prev(const FrameParams& p, uint32_t slo
     asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
 }
 
-__device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t slot, rv_f3 s,
+/* `tag` = the accumulation slot; in a batched launch (kBatch) slot | frame_in_batch << 26 */
+template <bool kBatch>
+__device__ __forceinline__ void finish_sample(const FrameParams& p, uint32_t tag, rv_f3 s,
                                               uint32_t rng, uint32_t raster = 0xFFFFFFFFu)
 {
+    if constexpr (kBatch)
+    {
+        /* aa == 1: sampled = (vec3(0) + sample) / 1. Parked until the resolve phase folds the
+         * frames of the pixel in order; written once, read once (streaming). */
+        const uint32_t slot = tag & RVPT_BATCH_SLOT_MASK, fi = tag >> RVPT_BATCH_SLOT_BITS;
+        __stcs(&p.samples[(size_t)fi * p.sample_stride + slot],
+               make_float4(0.0f + s.x, 0.0f + s.y, 0.0f + s.z, 0.0f));
+        return;
+    }
+    const uint32_t slot = tag;
     /* sampled = vec3(0); sampled += eval_integrator(...) */
     rv_f3 sum;
     if (p.pass == 0)
@@ -741,43 +766,58 @@ __device__ __forceinline__ void camera_ray(const FrameParams& p, float cx, float
 /* phases                                                                    */
 /* ======================================================================== */
 
-/* Launch L clears the counters of launch L+1 (and, on the first pass of a
- * frame, the stats of the next frame). Nobody reads them during this launch. */
-__device__ __forceinline__ void clear_next_stats(const FrameParams& p)
+/* The last CTA to leave a launch re-zeroes the wave counters for the next launch and, when the
+ * launch completes a frame / batch, publishes its per-bounce ray counts (device_scene.h,
+ * FrameCounters). Every thread of every CTA calls this as the last thing it does. */
+__device__ __forceinline__ void finish_launch(const FrameParams& p)
 {
-    if (blockIdx.x != 0 || p.pass != 0) return;
-    unsigned long long* a = p.ctr->stats[p.stats_set ^ 1u].active;
-    for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) a[i] = 0ull;
+    __shared__ uint32_t is_last;
+    __syncthreads(); /* every warp of the CTA is done with the counters */
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        is_last = atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (p.last_of_pass)
+    {
+        uint32_t* w = reinterpret_cast<uint32_t*>(&p.ctr->wave);
+        for (uint32_t i = threadIdx.x; i < sizeof(WaveCounters) / 4; i += blockDim.x) w[i] = 0u;
+    }
+    if (p.last_of_frame && threadIdx.x < 64u)
+    {
+        p.ctr->last.active[threadIdx.x] = __ldcg(&p.ctr->stats.active[threadIdx.x]);
+        p.ctr->stats.active[threadIdx.x] = 0ull;
+    }
+    if (threadIdx.x == 0)
+    {
+        if (p.last_of_frame) p.ctr->last_sets = p.n_batch ? p.n_batch : (uint32_t)p.aa;
+        p.ctr->done_ctas = 0u;
+    }
 }
 
-__device__ __forceinline__ void clear_next_counters(const FrameParams& p, bool stats_too = true)
-{
-    if (blockIdx.x != 0) return;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&p.ctr->wave[p.wave_set ^ 1u]);
-    for (uint32_t i = threadIdx.x; i < sizeof(WaveCounters) / 4; i += blockDim.x) w[i] = 0u;
-    if (stats_too) clear_next_stats(p);
-}
-
-/* Wave-size forecast from the previous launch: bit b of the result is set when the rays
- * traced at bounce b by the previous frame (pass 0; earlier passes of this frame otherwise)
- * fit the in-thread tail (<= tail_threshold per pass). A wave whose successor is forecast
+/* Wave-size forecast from the last completed frame / batch: bit b of the result is set when the
+ * rays it traced at bounce b, scaled to the full-image sample sets of THIS launch, fit the
+ * in-thread tail (<= tail_threshold). A wave whose successor is forecast
  * that small lets its few survivors run on inside their threads instead of queueing them,
  * which saves the grid barrier and the tail wave behind it. Scheduling only: a wrong
  * forecast (camera or scene just changed) costs lane utilisation for one frame, never a
- * different result. Must run before the first grid barrier (the stats set it reads is
- * zeroed for the next frame right after that). */
+ * different result. `last` is only written by the last CTA of a launch, so every CTA of this
+ * launch reads the same values. */
 __device__ __forceinline__ unsigned long long forecast_small_waves(const FrameParams& p, uint32_t* mostly_hits)
 {
     *mostly_hits = 0u;
     if (!p.use_forecast) return 0ull;
     const uint32_t lane = threadIdx.x & 31u;
-    const unsigned long long* a =
-        p.pass == 0 ? p.ctr->stats[p.stats_set ^ 1u].active : p.ctr->stats[p.stats_set].active;
-    const unsigned long long div = p.pass == 0 ? (unsigned long long)p.aa : (unsigned long long)p.pass;
-    const unsigned long long lim = (unsigned long long)p.tail_threshold * div;
-    const unsigned long long a_lo = a[lane], a_hi = a[lane + 32u];
-    const uint32_t lo = __ballot_sync(0xFFFFFFFFu, a_lo <= lim);
-    const uint32_t hi = __ballot_sync(0xFFFFFFFFu, a_hi <= lim);
+    const unsigned long long* a = p.ctr->last.active;
+    const unsigned long long sets_prev = max(1u, __ldcg(&p.ctr->last_sets));
+    const unsigned long long sets_now = p.n_batch ? p.n_batch : 1u;
+    const unsigned long long lim = (unsigned long long)p.tail_threshold * sets_prev;
+    const unsigned long long a_lo = __ldcg(&a[lane]), a_hi = __ldcg(&a[lane + 32u]);
+    const uint32_t lo = __ballot_sync(0xFFFFFFFFu, a_lo * sets_now <= lim);
+    const uint32_t hi = __ballot_sync(0xFFFFFFFFu, a_hi * sets_now <= lim);
     /* bounce rays (depth >= 1) against those that hit and went on (depth >= 2) */
     unsigned long long rays = (lane >= 1u ? a_lo : 0ull) + a_hi, hits = (lane >= 2u ? a_lo : 0ull) + a_hi;
 #pragma unroll
@@ -791,10 +831,10 @@ __device__ __forceinline__ unsigned long long forecast_small_waves(const FramePa
 }
 
 /* generation + bounce 0: compute_pass.comp:121-158, integrators.glsl:574-671 (i = 0) */
-template <bool kSmem, bool kRel, bool kOct>
+template <bool kSmem, bool kRel, bool kOct, bool kBatch = false>
 __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, bool sort)
 {
-    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    WaveCounters& wc = p.ctr->wave;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long traced = 0;
 
@@ -808,7 +848,10 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
      * stealing). The claim for the next chunk is issued before the current one
      * is traced, so its round trip to L2 is off the critical path. */
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t n_units = (p.n_chunks + kChunkGrain - 1) / kChunkGrain; /* claims are kChunkGrain chunks */
+    /* claims are kChunkGrain chunks; a batched launch hands out the chunks of all its frames,
+     * frame by frame (virtual chunk = frame_in_batch * n_chunks + chunk) */
+    const uint32_t n_vchunks = kBatch ? p.n_chunks * p.n_batch : p.n_chunks;
+    const uint32_t n_units = (n_vchunks + kChunkGrain - 1) / kChunkGrain;
     uint32_t shard = gwarp % RVPT_CHUNK_SHARDS;
     uint32_t dry = 0; /* shards found exhausted */
     uint32_t claim = 0;
@@ -836,9 +879,12 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
         if (unit >= n_units) break;
         if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
 
-      for (uint32_t c = unit * kChunkGrain, c_end = min(c + kChunkGrain, p.n_chunks); c < c_end; ++c)
+      for (uint32_t vc = unit * kChunkGrain, vc_end = min(vc + kChunkGrain, n_vchunks); vc < vc_end; ++vc)
       {
+        const uint32_t fi = kBatch ? vc / p.n_chunks : 0u;
+        const uint32_t c = kBatch ? vc - fi * p.n_chunks : vc;
         const uint32_t slot = c * 32u + lane;
+        const uint32_t tag = kBatch ? (slot | (fi << RVPT_BATCH_SLOT_BITS)) : slot;
         uint32_t x, y;
         slot_to_xy(p, slot, x, y);
         /* pixels of other integrators (split view) are rendered by k_modes */
@@ -849,10 +895,10 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
         PathState s;
         if (inside)
         {
-            prefetch_prev(p, slot);
+            if constexpr (!kBatch) prefetch_prev(p, slot);
             /* util.glsl:35-36; later samples of the frame continue the stream */
-            if (p.pass == 0)
-                s.rng = rv_wang_hash(x + y * p.W) + p.frame;
+            if (kBatch || p.pass == 0)
+                s.rng = rv_wang_hash(x + y * p.W) + (p.frame + fi);
             else
                 s.rng = __float_as_uint(p.carry[slot].w);
 
@@ -876,14 +922,14 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
                     sample = rv_make(0.0f, 0.0f, 0.0f);
                 }
             }
-            if (!alive) finish_sample(p, slot, sample, s.rng, y * p.W + x);
+            if (!alive) finish_sample<kBatch>(p, tag, sample, s.rng, y * p.W + x);
         }
         if (p.max_bounces > 0)
             traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside));
-        push_survivors(p, p.queue[0], wc.qcount[0], alive, slot, s, sort);
+        push_survivors(p, p.queue[0], wc.qcount[0], alive, tag, s, sort);
       }
     }
-    if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], traced);
+    if (lane == 0 && traced) atomicAdd(&p.ctr->stats.active[0], traced);
 }
 
 /* Resolve a claim issued earlier on `shard` of the sharded global work counters `ctr` into a unit
@@ -942,15 +988,15 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
  */
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_SHARDED 4u /* big wave, every 32-ray group claimed from the sharded counters */
-template <bool kSmem, bool kOct, bool kInThread>
+template <bool kSmem, bool kOct, bool kInThread, bool kBatch = false>
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
                                              const WaveGroups& wg, uint32_t mode, bool sort)
 {
-    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    WaveCounters& wc = p.ctr->wave;
     const PathQueue qin = p.queue[(b - 1) & 1];
     const PathQueue qout = p.queue[b & 1];
     const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long* active = p.ctr->stats[p.stats_set].active;
+    unsigned long long* active = p.ctr->stats.active;
     const bool spread = (mode & RVPT_WAVE_SPREAD) != 0;
     constexpr bool in_thread = kInThread; /* compile-time: keeps the queueing call sites lean */
     const bool sharded = (mode & RVPT_WAVE_SHARDED) != 0 && !spread;
@@ -1007,8 +1053,8 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
         uint32_t slot = 0;
         if (lane < L && i < wg.cnt[o])
         {
-            load_path(qin, o * p.queue_stride + i, s, slot);
-            prefetch_prev(p, slot);
+            load_path(qin, o * p.queue_stride + i, s, slot); /* slot: the path's tag */
+            if constexpr (!kBatch) prefetch_prev(p, slot);
             rv_f3 sample;
             for (int k = b;; ++k)
             {
@@ -1021,7 +1067,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
                 if (!in_thread || !alive) break;
                 if (k + 1 < RVPT_MAX_BOUNCE_STATS) atomicAdd(&active[k + 1], 1ull);
             }
-            if (!alive) finish_sample(p, slot, sample, s.rng);
+            if (!alive) finish_sample<kBatch>(p, slot, sample, s.rng);
         }
         if (!in_thread) push_survivors(p, qout, wc.qcount[b], alive, slot, s, sort);
     }
@@ -1146,9 +1192,90 @@ __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, u
 }
 
 /* ======================================================================== */
-/* k_frame: the whole frame (one aa pass) in ONE persistent cooperative launch */
+/* resolve phase of a batched launch                                          */
 /* ======================================================================== */
-template <bool kSmem, bool kRel, bool kOct>
+/* Folds the parked samples of frames frame .. frame + n_batch - 1 into the running mean, in
+ * frame order, with exactly the per-frame arithmetic of compute_pass.comp:146-148,161-166
+ * (in ACCUM_RGBA8 mode the temporal image is re-quantised after every frame, as the reference's
+ * UNORM8 image is), and writes the result image once. fc = per-frame (float(frame),
+ * 1/float(frame+1), float(min(frame,1))) in shared memory. Pure streaming: chunks are dealt
+ * statically. */
+__device__ __forceinline__ void resolve_phase(const FrameParams& p, const float* fc)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const bool u8 = (p.flags & RVPT_B200_FLAG_ACCUM_RGBA8) != 0;
+    for (uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < p.n_chunks; c += n_warps)
+    {
+        const uint32_t slot = c * 32u + lane;
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        if (!((x < p.W_eff) && (y < p.H_eff) && ((slot >> 8) * p.nranks + p.rank < p.n_tiles))) continue;
+        rv_f3 acc;
+        if (u8)
+        {
+            const uchar4 k = p.accum_u8[slot];
+            acc = rv_make(rv_unorm8_load(k.x), rv_unorm8_load(k.y), rv_unorm8_load(k.z));
+        }
+        else
+        {
+            const float4 a = p.accum_f32[slot];
+            acc = rv_make(a.x, a.y, a.z);
+        }
+        uchar4 q = make_uchar4(0, 0, 0, 0);
+        const float4* sp = p.samples + slot;
+        uint32_t fi = 0;
+        /* four loads in flight per thread */
+        for (; fi + 4u <= p.n_batch; fi += 4u)
+        {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldcs(sp + (size_t)(fi + k) * p.sample_stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const float* f = fc + 3u * (fi + k);
+                acc = fold_sample(acc, rv_make(v[k].x, v[k].y, v[k].z), f[0], f[1], f[2]);
+                if (u8)
+                {
+                    q = make_uchar4(dev_unorm8(acc.x), dev_unorm8(acc.y), dev_unorm8(acc.z), 0);
+                    acc = rv_make(rv_unorm8_load(q.x), rv_unorm8_load(q.y), rv_unorm8_load(q.z));
+                }
+            }
+        }
+        for (; fi < p.n_batch; ++fi)
+        {
+            const float4 v = __ldcs(sp + (size_t)fi * p.sample_stride);
+            const float* f = fc + 3u * fi;
+            acc = fold_sample(acc, rv_make(v.x, v.y, v.z), f[0], f[1], f[2]);
+            if (u8)
+            {
+                q = make_uchar4(dev_unorm8(acc.x), dev_unorm8(acc.y), dev_unorm8(acc.z), 0);
+                acc = rv_make(rv_unorm8_load(q.x), rv_unorm8_load(q.y), rv_unorm8_load(q.z));
+            }
+        }
+        if (u8)
+            p.accum_u8[slot] = q;
+        else
+        {
+            q = make_uchar4(dev_unorm8(acc.x), dev_unorm8(acc.y), dev_unorm8(acc.z), 0);
+            p.accum_f32[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+        }
+        store_result(p, slot, q, y * p.W + x);
+    }
+}
+
+/* ======================================================================== */
+/* k_frame: the whole frame (one aa pass) — or, with kBatch, a whole progressive batch of     */
+/* frames — in ONE persistent cooperative launch                               */
+/* ======================================================================== */
+/* kBatch (rvpt_b200_render_frames, aa == 1, Kajiya everywhere): the frames of a batch depend on
+ * each other only through each pixel's running mean, so their waves are merged — the primary
+ * wave generates the primary rays of ALL frames back to back, bounce wave b traces the depth-b
+ * rays of all frames (a queued path carries its frame in the slot tag), finished samples are
+ * parked, and one resolve phase folds them per pixel in frame order. The scene is staged once
+ * and the launch pays max_bounces grid barriers + one for the resolve, not that many per frame. */
+template <bool kSmem, bool kRel, bool kOct, bool kBatch>
 __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1158,11 +1285,9 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     __shared__ unsigned long long small_waves;
     __shared__ uint32_t ordered_bounce; /* bounce rays walk the front-to-back arrays this frame */
     __shared__ WaveGroups wg;
+    __shared__ float frame_consts[kBatch ? 3 * RVPT_MAX_BATCH : 1];
 
     stamp(p, 0);
-    /* with bounce waves, the next frame's stats set is zeroed after the first grid barrier:
-     * until then it still holds the previous frame's counts, which the forecast reads */
-    clear_next_counters(p, p.max_bounces < 2);
     if (threadIdx.x < 32)
     {
         uint32_t mostly_hits;
@@ -1173,6 +1298,17 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
             ordered_bounce = mostly_hits;
         }
     }
+    if constexpr (kBatch)
+    {
+        if (threadIdx.x < p.n_batch)
+        {
+            /* compute_pass.comp:146-148,161-163; rvpt.cpp:102-111 (current_frame++) */
+            const uint32_t f = p.frame + threadIdx.x;
+            frame_consts[3 * threadIdx.x + 0] = (float)f;
+            frame_consts[3 * threadIdx.x + 1] = 1.0f / (float)(f + 1u);
+            frame_consts[3 * threadIdx.x + 2] = (float)(f < 1u ? f : 1u);
+        }
+    }
     const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar, &ordered_bounce);
     if constexpr (!kSmem) __syncthreads(); /* the global path stages nothing: publish the forecast */
     stamp(p, 1);
@@ -1180,25 +1316,29 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     /* closed scenes (most bounce rays hit something) queue their survivors by direction octant;
      * ordered_bounce is visible to everybody since the barriers of setup_scene */
     const bool sort = p.queue_stride != 0u && ordered_bounce != 0u;
-    primary_phase<kSmem, kRel, kOct>(p, sc, sort);
+    primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
     stamp(p, 2);
 
-    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    WaveCounters& wc = p.ctr->wave;
+    bool synced = false; /* a grid barrier has been passed since the last sample was parked */
     for (int b = 1; b < p.max_bounces; ++b)
     {
         grid.sync(); /* wave b-1 is complete: its survivor count is final */
-        if (b == 1) clear_next_stats(p);
         stamp(p, 2 * b + 1);
         uint32_t my_count;
         const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
-        if (count == 0) break;
+        if (count == 0)
+        {
+            synced = true;
+            break;
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
-            atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
+            atomicAdd(&p.ctr->stats.active[b], (unsigned long long)count);
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
         prepare_wave(wg, my_count, count, count <= 64u * n_warps);
         if (count <= p.tail_threshold)
         {
-            bounce_phase<kSmem, kOct, true>(p, sc, b, wg, RVPT_WAVE_SPREAD, sort);
+            bounce_phase<kSmem, kOct, true, kBatch>(p, sc, b, wg, RVPT_WAVE_SPREAD, sort);
             stamp(p, 2 * b + 2);
             break;
         }
@@ -1211,348 +1351,21 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull))
         {
             /* forecast: wave b+1 would be a tail anyway — its rays finish here, in their threads */
-            bounce_phase<kSmem, kOct, true>(p, sc, b, wg, deal, sort);
+            bounce_phase<kSmem, kOct, true, kBatch>(p, sc, b, wg, deal, sort);
             stamp(p, 2 * b + 2);
             break;
         }
-        bounce_phase<kSmem, kOct, false>(p, sc, b, wg, deal, sort);
+        bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
         stamp(p, 2 * b + 2);
     }
-}
-
-/* ======================================================================== */
-/* k_flow: the whole frame as ONE barrier-free stream of work per SM          */
-/* ======================================================================== */
-/*
- * k_frame separates the bounce waves with grid barriers; the timeline
- * (profiles/) shows 13-16 % of a frame waiting at them. Here every CTA keeps
- * its own wavefront queue — a ring of RVPT_FLOW_RING 64-byte SoA path records
- * in HBM (L2-resident), produced and consumed by the warps of that CTA only,
- * so all synchronisation is shared-memory atomics inside the CTA and there is
- * no grid-wide barrier at all:
- *
- *   warp loop:  a full 32-ray group is committed in my CTA's ring -> pop it, trace one
- *               bounce, terminated lanes accumulate, survivors are appended
- *               (depth + 1);
- *               else claim a 32-pixel primary chunk (global sharded counter, as in
- *               k_frame), generate + trace bounce 0, append survivors (depth 1);
- *               else (no primary work left anywhere, nobody in my CTA can still
- *               append) pop the final partial group and run it to the end in-thread;
- *               ring empty -> exit.
- *
- * Popping has priority, so a ring holds little more than one group per warp; primary
- * claims stop while the backlog exceeds RVPT_FLOW_LIMIT, which bounds it strictly
- * (LIMIT + 32 warps x 32 appends in flight < RING). Entry (ring index) i lives in group
- * i / 32; gstate[group % GROUPS] = generation << 8 | committed entries: appenders wait
- * for their group's generation (the previous occupant was consumed — never the case in
- * practice), write, fence, add their count; the consumer of a group bumps the generation
- * after its loads. Results do not depend on any of this: a path carries its pixel slot,
- * RNG state and depth, and each pixel is accumulated exactly once per pass.
- */
-#define RVPT_FLOW_GROUPS (RVPT_FLOW_RING / 32u)
-#define RVPT_FLOW_LIMIT (RVPT_FLOW_RING / 2u)
-
-struct FlowShared
-{
-    uint32_t lock;      /* guards the pop decision (rd, tail handling) */
-    uint32_t res;       /* entries reserved so far (monotonic) */
-    uint32_t rd;        /* groups popped so far (monotonic) */
-    uint32_t active;    /* work units in flight that may still append */
-    uint32_t pad[4];
-    uint32_t gstate[RVPT_FLOW_GROUPS];
-    uint32_t hist[RVPT_MAX_BOUNCE_STATS]; /* rays traced at depth k >= 1 by this CTA */
-};
-
-enum : uint32_t { FLOW_POP = 1, FLOW_POP_TAIL = 2, FLOW_PRIMARY = 3, FLOW_WAIT = 4, FLOW_EXIT = 5, FLOW_RETRY = 6 };
-
-/* acquire/release fence at CTA scope (the MEMBAR.SC of __threadfence_block is not needed) */
-__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* a)
-{
-    return *reinterpret_cast<const volatile uint32_t*>(a);
-}
-
-/* Append the surviving lanes (depth = index of the bounce they trace next). */
-__device__ __forceinline__ void flow_push(const FrameParams& p, FlowShared& fs, bool alive, uint32_t slot,
-                                          const PathState& s, uint32_t depth)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
-    if (mask == 0) return;
-    const uint32_t cnt = (uint32_t)__popc(mask);
-    uint32_t base = 0;
-    if (lane == 0)
+    if constexpr (kBatch)
     {
-        base = atomicAdd(&fs.res, cnt);
-        /* ring slots of both groups touched must have been consumed one lap ago */
-        const uint32_t g0 = base >> 5, g1 = (base + cnt - 1u) >> 5;
-        uint32_t spins = 0;
-        while ((ld_volatile_shared(&fs.gstate[g0 % RVPT_FLOW_GROUPS]) >> 8) != ((g0 / RVPT_FLOW_GROUPS) & 0xFFFFFFu) ||
-               (ld_volatile_shared(&fs.gstate[g1 % RVPT_FLOW_GROUPS]) >> 8) != ((g1 / RVPT_FLOW_GROUPS) & 0xFFFFFFu))
-        {
-            if (++spins > (1u << 22)) __trap(); /* never hang the GPU */
-            __nanosleep(32);
-        }
+        if (!synced) grid.sync(); /* every sample of the batch is parked */
+        stamp(p, RVPT_TIMELINE_SLOTS - 2u);
+        resolve_phase(p, frame_consts);
+        stamp(p, RVPT_TIMELINE_SLOTS - 1u);
     }
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (alive)
-    {
-        const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-        const uint32_t i = blockIdx.x * RVPT_FLOW_RING + (e % RVPT_FLOW_RING);
-        const PathQueue& q = p.queue[0];
-        __stcs(&q.q0[i], make_float4(s.o.x, s.o.y, s.o.z, __uint_as_float(slot)));
-        __stcs(&q.q1[i], make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.rng)));
-        __stcs(&q.q2[i], make_float4(s.thr.x, s.thr.y, s.thr.z, __uint_as_float(depth)));
-        __stcs(&q.q3[i], make_float4(s.col.x, s.col.y, s.col.z, 0.0f));
-        fence_cta(); /* the records before the commit, for the warps of this CTA */
-    }
-    __syncwarp();
-    if (lane == 0)
-    {
-        const uint32_t g0 = base >> 5;
-        const uint32_t n0 = min(cnt, (g0 + 1u) * 32u - base);
-        atomicAdd(&fs.gstate[g0 % RVPT_FLOW_GROUPS], n0);
-        if (cnt > n0) atomicAdd(&fs.gstate[(g0 + 1u) % RVPT_FLOW_GROUPS], cnt - n0);
-    }
-}
-
-__device__ __forceinline__ void flow_retire(FlowShared& fs)
-{
-    __syncwarp();
-    if ((threadIdx.x & 31u) == 0) atomicSub(&fs.active, 1u); /* after this warp's commits, in program order */
-}
-
-template <bool kSmem, bool kRel, bool kOct>
-__device__ __forceinline__ void flow_loop(const FrameParams& p, const SceneViewT<kSmem>& sc, FlowShared& fs)
-{
-    WaveCounters& wc = p.ctr->wave[p.wave_set];
-    const uint32_t lane = threadIdx.x & 31u;
-    const PathQueue& q = p.queue[0];
-    uint32_t shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_CHUNK_SHARDS;
-    uint32_t traced = 0; /* primary rays of this warp: < 2^32 per launch */
-    uint32_t idle_spins = 0;
-    /* The claim for the next primary chunk is always in flight (issued before the current
-     * unit is processed), so its round trip to the L2 atomic unit is off the critical path.
-     * A warp holding a claim is counted in `active`: it may still append. */
-    bool holding = true; /* the first claim of every warp is counted in fs.active by k_flow's set-up */
-    uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
-
-    for (;;)
-    {
-        uint32_t kind = 0, g = 0, n = 0;
-        if (lane == 0)
-        {
-            /* Lock-free decision on shared-memory words (volatile + atomics; the shared
-             * pipeline executes one thread's accesses in order). A unit is counted in
-             * `active` BEFORE it is claimed, so active == 0 proves nothing can append. */
-            g = ld_volatile_shared(&fs.rd);
-            const uint32_t st = ld_volatile_shared(&fs.gstate[g % RVPT_FLOW_GROUPS]);
-            if (st == ((((g / RVPT_FLOW_GROUPS) & 0xFFFFFFu) << 8) | 32u))
-            {
-                atomicAdd(&fs.active, 1u);
-                if (atomicCAS(&fs.rd, g, g + 1u) == g)
-                {
-                    kind = FLOW_POP;
-                    n = 32u;
-                }
-                else
-                {
-                    atomicSub(&fs.active, 1u); /* another warp took it: look again */
-                    kind = FLOW_RETRY;
-                }
-            }
-            else if (!holding)
-            {
-                /* drain: the final partial group. Serialised by a lock; no pop can race with
-                 * it, because a pop needs a full head group and nobody can append any more. */
-                kind = FLOW_WAIT;
-                if (ld_volatile_shared(&fs.active) == 0u &&
-                    ld_volatile_shared(&fs.res) == ld_volatile_shared(&fs.rd) * 32u)
-                    kind = FLOW_EXIT; /* nobody can append any more and the ring is empty: final */
-                else if (ld_volatile_shared(&fs.active) == 0u && atomicCAS(&fs.lock, 0u, 1u) == 0u)
-                {
-                    g = ld_volatile_shared(&fs.rd);
-                    n = ld_volatile_shared(&fs.res) - g * 32u;
-                    if (ld_volatile_shared(&fs.active) != 0u || n >= 32u)
-                        kind = FLOW_RETRY; /* raced with the last commit: a full group is poppable */
-                    else if (n == 0u)
-                        kind = FLOW_EXIT;
-                    else
-                    {
-                        atomicAdd(&fs.active, 1u);
-                        *reinterpret_cast<volatile uint32_t*>(&fs.res) = (g + 1u) * 32u; /* rest of the group stays unused */
-                        *reinterpret_cast<volatile uint32_t*>(&fs.rd) = g + 1u;
-                        kind = FLOW_POP_TAIL;
-                    }
-                    atomicExch(&fs.lock, 0u);
-                }
-            }
-            else if (ld_volatile_shared(&fs.res) - g * 32u >= RVPT_FLOW_LIMIT)
-                kind = FLOW_WAIT; /* backlog bound: let the head group commit first */
-            else
-                kind = FLOW_PRIMARY; /* the held claim is already counted in `active` */
-        }
-        kind = __shfl_sync(0xFFFFFFFFu, kind, 0);
-        g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
-        if (kind == FLOW_EXIT) break;
-        if (kind == FLOW_RETRY) continue;
-        /* acquire side of the commit counters: the records of a popped group were released
-         * by their writers' fence + shared-memory atomic */
-        if (kind == FLOW_POP || kind == FLOW_POP_TAIL) fence_cta();
-        if (kind == FLOW_WAIT)
-        {
-            /* Waiting warps must not take issue slots from the warps they wait for: sleep with
-             * exponential back-off, 0.25 .. 2 us (a polling warp costs ~45 instructions a round). */
-            if (++idle_spins > (1u << 20)) __trap(); /* ~2 s: never hang the GPU */
-            __nanosleep((256u << min(idle_spins - 1u, 3u)) + ((threadIdx.x >> 5) * 37u & 255u));
-            continue;
-        }
-        idle_spins = 0;
-
-        if (kind == FLOW_PRIMARY)
-        {
-            const uint32_t c = resolve_claim(wc.chunk_ctr, p.n_chunks, shard, claim);
-            if (c == 0xFFFFFFFFu)
-            {
-                holding = false; /* this warp only pops from now on */
-                flow_retire(fs);
-                continue;
-            }
-            if (lane == 0)
-            {
-                atomicAdd(&fs.active, 1u);
-                claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
-            }
-            const uint32_t slot = c * 32u + lane;
-            uint32_t x, y;
-            slot_to_xy(p, slot, x, y);
-            const bool inside = (x < p.W_eff) && (y < p.H_eff) &&
-                                ((slot >> 8) * p.nranks + p.rank < p.n_tiles) &&
-                                (p.all_kajiya || integrator_of(p, x, y) == 9);
-            bool alive = false;
-            PathState s;
-            if (inside)
-            {
-                prefetch_prev(p, slot);
-                if (p.pass == 0)
-                    s.rng = rv_wang_hash(x + y * p.W) + p.frame;
-                else
-                    s.rng = __float_as_uint(p.carry[slot].w);
-                const float jx = rv_rand(&s.rng);
-                const float jy = rv_rand(&s.rng);
-                const float cx = ((float)x + jx) * p.inv_dim_x;
-                float cy = ((float)y + jy) * p.inv_dim_y;
-                cy = 1.0f - cy;
-                camera_ray(p, cx, cy, s.o, s.d);
-                s.thr = rv_make(1.0f, 1.0f, 1.0f);
-                s.col = rv_make(0.0f, 0.0f, 0.0f);
-                rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
-                if (p.max_bounces > 0)
-                {
-                    alive = kajiya_step<kSmem, kRel, kOct>(sc, s, sample);
-                    if (alive && p.max_bounces == 1)
-                    {
-                        alive = false; /* integrators.glsl:674-675 */
-                        sample = rv_make(0.0f, 0.0f, 0.0f);
-                    }
-                }
-                if (!alive) finish_sample(p, slot, sample, s.rng, y * p.W + x);
-            }
-            if (p.max_bounces > 0)
-                traced += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, inside));
-            flow_push(p, fs, alive, slot, s, 1u);
-            flow_retire(fs);
-            continue;
-        }
-
-        /* FLOW_POP / FLOW_POP_TAIL: group g, n entries */
-        {
-            const bool mine = lane < n;
-            bool alive = false;
-            PathState s;
-            uint32_t slot = 0, depth = 0, dep = 0;
-            if (mine)
-            {
-                const uint32_t i = blockIdx.x * RVPT_FLOW_RING + ((g * 32u + lane) % RVPT_FLOW_RING);
-                const float4 a0 = __ldcg(&q.q0[i]);
-                const float4 a1 = __ldcg(&q.q1[i]);
-                const float4 a2 = __ldcg(&q.q2[i]);
-                const float4 a3 = __ldcg(&q.q3[i]);
-                s.o = rv_make(a0.x, a0.y, a0.z);
-                slot = __float_as_uint(a0.w);
-                s.d = rv_make(a1.x, a1.y, a1.z);
-                s.rng = __float_as_uint(a1.w);
-                s.thr = rv_make(a2.x, a2.y, a2.z);
-                depth = __float_as_uint(a2.w);
-                s.col = rv_make(a3.x, a3.y, a3.z);
-                prefetch_prev(p, slot);
-                /* the ring slots are handed back only after the four loads have returned: the
-                 * new generation value is made data-dependent on them (lane 0 is always `mine`,
-                 * and a warp-wide load retires as one instruction) */
-                asm volatile("{\n\t.reg .b32 t;\n\t"
-                             "or.b32 t, %1, %2;\n\tor.b32 t, t, %3;\n\tor.b32 t, t, %4;\n\t"
-                             "and.b32 %0, t, 0;\n\t}"
-                             : "=r"(dep)
-                             : "r"(__float_as_uint(a0.w)), "r"(__float_as_uint(a1.w)),
-                               "r"(__float_as_uint(a2.w)), "r"(__float_as_uint(a3.w)));
-            }
-            if (lane == 0)
-                atomicExch(&fs.gstate[g % RVPT_FLOW_GROUPS],
-                           ((((g / RVPT_FLOW_GROUPS) + 1u) & 0xFFFFFFu) << 8) + dep);
-            if (mine)
-            {
-                /* rays traced per depth: one shared-memory atomic per distinct depth in the group */
-                const uint32_t peers = __match_any_sync(n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u), depth);
-                if (lane == (uint32_t)(__ffs(peers) - 1) && depth < RVPT_MAX_BOUNCE_STATS)
-                    atomicAdd(&fs.hist[depth], (uint32_t)__popc(peers));
-                rv_f3 sample;
-                for (uint32_t k = depth;; ++k)
-                {
-                    if (k != depth && k < RVPT_MAX_BOUNCE_STATS) atomicAdd(&fs.hist[k], 1u);
-                    alive = kajiya_step<kSmem, false, kOct>(sc, s, sample);
-                    if (alive && (int)k == p.max_bounces - 1)
-                    {
-                        alive = false; /* integrators.glsl:674-675: col is discarded */
-                        sample = rv_make(0.0f, 0.0f, 0.0f);
-                    }
-                    if (kind != FLOW_POP_TAIL || !alive) break;
-                }
-                if (!alive) finish_sample(p, slot, sample, s.rng);
-            }
-            if (kind == FLOW_POP) flow_push(p, fs, alive, slot, s, depth + 1u);
-            flow_retire(fs);
-        }
-    }
-    if (lane == 0 && traced) atomicAdd(&p.ctr->stats[p.stats_set].active[0], (unsigned long long)traced);
-}
-
-template <bool kSmem, bool kRel, bool kOct>
-__global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_flow(const FrameParams p)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    __shared__ FlowShared fs;
-
-    stamp(p, 0);
-    for (uint32_t i = threadIdx.x; i < sizeof(FlowShared) / 4u; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(&fs)[i] = 0u;
-    __syncthreads();
-    if (threadIdx.x == 0) fs.active = blockDim.x >> 5; /* every warp starts out holding one primary claim */
-    clear_next_counters(p);
-    __syncthreads();
-    const SceneViewT<kSmem> sc = setup_scene<kSmem, kRel, kOct>(p, smem, &bar);
-    stamp(p, 1);
-
-    flow_loop<kSmem, kRel, kOct>(p, sc, fs);
-    stamp(p, 2);
-
-    __syncthreads();
-    if (threadIdx.x < RVPT_MAX_BOUNCE_STATS && threadIdx.x >= 1u && fs.hist[threadIdx.x])
-        atomicAdd(&p.ctr->stats[p.stats_set].active[threadIdx.x], (unsigned long long)fs.hist[threadIdx.x]);
-    stamp(p, 3);
+    finish_launch(p);
 }
 
 /* ======================================================================== */
@@ -1563,7 +1376,6 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    clear_next_counters(p);
     SceneViewT<kSmem> sc;
     if constexpr (kSmem)
     {
@@ -1573,6 +1385,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     else
         sc = make_view<false>(p.scene, p.layout);
     primary_phase<kSmem, false, false>(p, sc, p.queue_stride != 0u);
+    finish_launch(p);
 }
 
 template <bool kSmem>
@@ -1581,13 +1394,17 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
 
-    WaveCounters& wc = p.ctr->wave[p.wave_set];
+    WaveCounters& wc = p.ctr->wave;
     __shared__ WaveGroups wg;
     uint32_t my_count;
     const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
-    if (count == 0) return; /* an empty wave costs nothing but the launch */
+    if (count == 0) /* an empty wave costs nothing but the launch */
+    {
+        finish_launch(p);
+        return;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
-        atomicAdd(&p.ctr->stats[p.stats_set].active[b], (unsigned long long)count);
+        atomicAdd(&p.ctr->stats.active[b], (unsigned long long)count);
 
     SceneViewT<kSmem> sc;
     if constexpr (kSmem)
@@ -1601,6 +1418,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     prepare_wave(wg, my_count, count, count <= 64u * n_warps);
     bounce_phase<kSmem, false, false>(p, sc, b, wg, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u,
                                       p.queue_stride != 0u);
+    finish_launch(p);
 }
 
 /* ======================================================================== */
@@ -2051,14 +1869,14 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 cudaError_t configure_kernels(size_t max_dynamic_smem)
 {
     cudaError_t e;
-    if ((e = set_smem(k_frame<true, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_frame<true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_frame<true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_frame<true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_flow<true, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_flow<true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_flow<true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
-    if ((e = set_smem(k_flow<true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, true, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, true, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, true, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, false, false>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, true, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, true, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, true, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
+    if ((e = set_smem(k_frame<true, false, false, true>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_primary<true>, max_dynamic_smem)) != cudaSuccess) return e;
     if ((e = set_smem(k_bounce<true>, max_dynamic_smem)) != cudaSuccess) return e;
     return set_smem(k_modes<true>, max_dynamic_smem);
@@ -2080,15 +1898,22 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
 {
     const size_t dyn = smem ? scene_bytes : 0;
     cudaError_t e;
+    int classic = 0, batch = 0;
     if (smem)
     {
         const size_t fdyn = frame_smem_bytes(scene_bytes, n_nodes, n_tris, oct);
         if (oct)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
-                                                              k_frame<true, true, true>, kThreads, fdyn);
+        {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&classic, k_frame<true, true, true, false>, kThreads, fdyn);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&batch, k_frame<true, true, true, true>, kThreads, fdyn);
+        }
         else
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
-                                                              k_frame<true, true, false>, kThreads, fdyn);
+        {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&classic, k_frame<true, true, false, false>, kThreads, fdyn);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&batch, k_frame<true, true, false, true>, kThreads, fdyn);
+        }
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<true>,
                                                           kThreads, dyn);
@@ -2098,8 +1923,9 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
     }
     else
     {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(frame_ctas_per_sm,
-                                                          k_frame<false, false, false>, kThreads, dyn);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&classic, k_frame<false, false, false, false>, kThreads, dyn);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&batch, k_frame<false, false, false, true>, kThreads, dyn);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(primary_ctas_per_sm, k_primary<false>,
                                                           kThreads, dyn);
@@ -2107,62 +1933,29 @@ cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bou
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bounce_ctas_per_sm, k_bounce<false>,
                                                           kThreads, dyn);
     }
+    /* one grid size for both flavours of the frame kernel (tail thresholds, timeline) */
+    *frame_ctas_per_sm = classic < batch ? classic : batch;
     return e;
 }
 
+template <bool kBatch>
+static const void* frame_kernel(const FrameParams& p, bool smem, bool oct)
+{
+    if (!smem) return (const void*)k_frame<false, false, false, kBatch>;
+    /* the ortho camera has a different origin per ray: no shared-origin copies */
+    const bool rel = p.camera_mode != 1;
+    if (oct)
+        return rel ? (const void*)k_frame<true, true, true, kBatch> : (const void*)k_frame<true, false, true, kBatch>;
+    return rel ? (const void*)k_frame<true, true, false, kBatch> : (const void*)k_frame<true, false, false, kBatch>;
+}
+
+/* p.n_batch > 0 selects the batched flavour (frames p.frame .. p.frame + n_batch - 1) */
 cudaError_t launch_frame(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st)
 {
     void* args[] = {const_cast<FrameParams*>(&p)};
-    const void* k;
-    size_t dyn = 0;
-    if (smem)
-    {
-        dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris, oct);
-        /* the ortho camera has a different origin per ray: no shared-origin copies */
-        const bool rel = p.camera_mode != 1;
-        if (oct)
-            k = rel ? (const void*)k_frame<true, true, true> : (const void*)k_frame<true, false, true>;
-        else
-            k = rel ? (const void*)k_frame<true, true, false> : (const void*)k_frame<true, false, false>;
-    }
-    else
-        k = (const void*)k_frame<false, false, false>;
+    const size_t dyn = smem ? frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris, oct) : 0;
+    const void* k = p.n_batch ? frame_kernel<true>(p, smem, oct) : frame_kernel<false>(p, smem, oct);
     return cudaLaunchCooperativeKernel(k, dim3(grid), dim3(kThreads), args, dyn, st);
-}
-
-/* k_flow needs no co-residency (no CTA ever waits for another CTA): plain launch */
-cudaError_t launch_flow(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st)
-{
-    if (smem)
-    {
-        const size_t dyn = frame_smem_bytes(p.layout.bytes, p.layout.n_nodes, p.layout.n_tris, oct);
-        const bool rel = p.camera_mode != 1;
-        if (oct && rel)
-            k_flow<true, true, true><<<grid, kThreads, dyn, st>>>(p);
-        else if (oct)
-            k_flow<true, false, true><<<grid, kThreads, dyn, st>>>(p);
-        else if (rel)
-            k_flow<true, true, false><<<grid, kThreads, dyn, st>>>(p);
-        else
-            k_flow<true, false, false><<<grid, kThreads, dyn, st>>>(p);
-    }
-    else
-        k_flow<false, false, false><<<grid, kThreads, 0, st>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t flow_occupancy(int* ctas_per_sm, bool smem, bool oct, size_t scene_bytes, uint32_t n_nodes,
-                           uint32_t n_tris)
-{
-    if (!smem)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<false, false, false>,
-                                                             kThreads, 0);
-    const size_t dyn = frame_smem_bytes(scene_bytes, n_nodes, n_tris, oct);
-    if (oct)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<true, true, true>,
-                                                             kThreads, dyn);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_flow<true, true, false>, kThreads,
-                                                         dyn);
 }
 
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st)

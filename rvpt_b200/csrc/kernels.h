@@ -15,9 +15,6 @@ size_t frame_smem_bytes(size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris, b
 cudaError_t occupancy(int* frame_ctas_per_sm, int* primary_ctas_per_sm, int* bounce_ctas_per_sm,
                       bool smem, bool oct, size_t scene_bytes, uint32_t n_nodes, uint32_t n_tris);
 cudaError_t launch_frame(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st);
-cudaError_t launch_flow(const FrameParams& p, bool smem, bool oct, int grid, cudaStream_t st);
-cudaError_t flow_occupancy(int* ctas_per_sm, bool smem, bool oct, size_t scene_bytes, uint32_t n_nodes,
-                           uint32_t n_tris);
 cudaError_t launch_primary(const FrameParams& p, bool smem, int grid, cudaStream_t st);
 cudaError_t launch_bounce(const FrameParams& p, int b, bool smem, int grid, cudaStream_t st);
 cudaError_t launch_modes(const FrameParams& p, bool smem, int grid, cudaStream_t st);

@@ -171,7 +171,8 @@ class Engine:
         while active and active[-1] == 0:
             active.pop()
         return {"samples": int(st.samples), "segments": int(st.segments), "active": active,
-                "kernel_launches": int(st.kernel_launches), "traversal_order": int(st.traversal_order)}
+                "kernel_launches": int(st.kernel_launches), "traversal_order": int(st.traversal_order),
+                "frames": int(st.frames)}
 
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.rvpt_b200_set_profiling(self._ctx, int(enabled)))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(rv):
     for name in names:
         assert hasattr(lib, name), f"{name} declared in rvpt_abi.h but not exported"
         assert name in rv._lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rvpt_b200_abi_version() == 1
+    assert lib.rvpt_b200_abi_version() == 2
     assert b"sm_100a" in lib.rvpt_b200_build_info()
 
 

@@ -179,7 +179,12 @@ def test_multi_frame_launch_equals_frame_by_frame(rv, oracle_mod, cornell, aa):
     _assert_bit_equal(batch.read_accum_f32(), ora.accum, "multi-frame launch vs oracle")
     _assert_bit_equal(batch.read_accum_f32(), one.read_accum_f32(), "multi-frame vs frame by frame")
     assert np.array_equal(batch.read_output_rgba8(), one.read_output_rgba8())
-    assert batch.stats()["active"] == ora.active_list()  # stats of the last frame
+    st = batch.stats()
+    if aa == 1:  # batched launch: the counters cover its 4 frames (3..6)
+        assert st["frames"] == 4 and st["kernel_launches"] == 1
+        assert st["samples"] == 4 * W * H
+    else:        # aa > 1 is sequential per pixel: frame by frame, stats of the last frame
+        assert st["frames"] == 1 and st["active"] == ora.active_list()
 
 
 def test_unfused_waves_equal_fused_frame_kernel(rv, oracle_mod, cornell):
@@ -304,8 +309,8 @@ def test_unsupported_and_error_paths(rv, builtin):
 
 
 def test_full_size_1080p_properties(rv, oracle_mod, builtin):
-    """BASELINE config 2 at full size: a band of rows against the oracle,
-    sample count, and frame-order independence of the tile scheduler (two
+    """BASELINE config 2 at full size, three progressive frames launched one by one: every
+    pixel against the oracle, sample count, and independence of the tile scheduler (two
     engines, same frames -> identical images: no float atomics anywhere)."""
     W, H = 1920, 1080
     cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
@@ -314,19 +319,48 @@ def test_full_size_1080p_properties(rv, oracle_mod, builtin):
     e2 = rv.Engine(W, H)
     e2.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
     ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
-    y0, y1 = 500, 532
     for f in range(3):
         rs = rv.default_settings(frame=f)
         e1.render_frame(rs, cam)
         e2.render_frame(rs, cam)
-        ora.render_frame(rs, cam, y0, y1)
+        ora.render_frame(rs, cam)
     g = e1.read_accum_f32()
-    _assert_bit_equal(g[y0:y1], ora.accum[y0:y1], "1080p rows 500..531")
+    _assert_bit_equal(g, ora.accum, "1080p, 3 frames, every pixel")
     _assert_bit_equal(g, e2.read_accum_f32(), "determinism across engines")
     st = e1.stats()
     assert st["samples"] == W * H
     assert st["segments"] == sum(st["active"])
+    assert st["active"] == ora.active_list()
     assert g[1079].any(), "rows >= 1072 are rendered unless REFERENCE_DISPATCH is set"
+
+
+@pytest.mark.parametrize("config", ["C2", "C3"])
+def test_stated_configs_full_frames_64(rv, oracle_mod, builtin, cornell, config):
+    """C2 (built-in scene) and C3 (Cornell box + mesh, mirror and dielectric
+    blocks) at 1920x1080, 8 bounces, frames 0..63 — EVERY pixel of the float32 running mean and
+    of the rgba8 image against the oracle, through rvpt_b200_render_frames (batched launches)."""
+    W, H, N = 1920, 1080, 64
+    prep, pose, fov = (builtin, DEFAULT_POSE, 90.0) if config == "C2" else (cornell, CORNELL_POSE, 60.0)
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    eng.render_frames(rv.default_settings(frame=0), cam, N)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    want_active = np.zeros(64, np.uint64)
+    frames_last = eng.stats()["frames"]
+    for f in range(N):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+        if f >= N - frames_last:
+            want_active += ora.active
+    g = eng.read_accum_f32()
+    rel = np.abs(g - ora.accum) / np.maximum(np.abs(ora.accum), 1e-6)
+    assert rel.max() <= 1e-4  # BASELINE.json north_star tolerance
+    _assert_bit_equal(g, ora.accum, f"{config} after {N} frames, every pixel")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    st = eng.stats()
+    got = np.zeros(64, np.uint64)
+    got[:len(st["active"])] = st["active"]
+    assert np.array_equal(got, want_active), "per-bounce ray counts of the last launch"
 
 
 def test_cpp_headless_driver_matches_python_host(rv, builtin, tmp_path):
@@ -428,16 +462,18 @@ def test_c4_full_size_4k_partition(rv, oracle_mod, builtin):
         eng.render_frames(rv.default_settings(frame=0), cam, 2)
         acc += eng.read_accum_f32()
         rgba += eng.read_output_rgba8()
-        samples += eng.stats()["samples"]
+        st = eng.stats()
+        assert st["frames"] == 2  # one batched launch
+        samples += st["samples"]
         eng.close()
     _assert_bit_equal(acc, want, "4K, 8 ranks")
     assert np.array_equal(rgba, want_rgba)
-    assert samples == W * H
+    assert samples == 2 * W * H
     ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
-    y0, y1 = 1200, 1216
     for f in range(2):
-        ora.render_frame(rv.default_settings(frame=f), cam, y0, y1)
-    _assert_bit_equal(want[y0:y1], ora.accum[y0:y1], "4K rows vs oracle")
+        ora.render_frame(rv.default_settings(frame=f), cam)
+    _assert_bit_equal(want, ora.accum, "4K full frames vs oracle")
+    assert np.array_equal(want_rgba, ora.result)
 
 
 @pytest.mark.parametrize("size", [(1, 1), (7, 5), (16, 16), (17, 33)])
@@ -505,72 +541,6 @@ def test_frame_kernel_timeline(rv, builtin):
     eng.set_timeline(False)
     eng.render_frame(rv.default_settings(frame=1), cam)
     assert eng.timeline().size == 0
-
-
-# ---- k_flow: the barrier-free frame kernel (RVPT_B200_FLAG_FLOW) ----------------------------
-
-@pytest.mark.parametrize("case", ["builtin_default", "builtin_pinned", "cornell", "cornell_aa2",
-                                  "cornell_b1", "cornell_b2", "cornell_b16", "ortho", "rgba8",
-                                  "no_octants", "global_path"])
-def test_flow_kernel_bit_exact(rv, oracle_mod, builtin, cornell, case):
-    """Every SM streaming its own wavefront queue (no grid barriers) is the same computation:
-    bit-exact against the oracle, same per-bounce ray counts."""
-    from rvpt_b200 import _lib
-    F = _lib.FLAG_FLOW
-    kw = dict(frames=2)
-    prep, W, H, pose, flags = cornell, 176, 128, CORNELL_POSE, F
-    if case.startswith("builtin"):
-        prep, W, H = builtin, 256, 256
-        pose = DEFAULT_POSE if case == "builtin_default" else PINNED_POSE
-    elif case == "cornell":
-        kw.update(frames=3, fov=60.0)
-    elif case == "cornell_aa2":
-        kw.update(fov=60.0, aa=2)
-    elif case.startswith("cornell_b"):
-        kw.update(fov=60.0, max_bounces=int(case[9:]))
-    elif case == "ortho":
-        prep, pose = builtin, PINNED_POSE
-        kw.update(camera_mode=1)
-    elif case == "rgba8":
-        prep, pose, flags = builtin, DEFAULT_POSE, F | _lib.FLAG_ACCUM_RGBA8
-    elif case == "no_octants":
-        kw.update(fov=60.0)
-        flags = F | _lib.FLAG_NO_OCTANTS
-    if case == "global_path":
-        from conftest import PreparedScene
-        prep = PreparedScene(rv, rv.displaced_sphere_scene(20000))
-        W, H, pose = 160, 96, (0.0, 1.2, -3.0)
-        kw.update(frames=2, fov=60.0)
-    oflags = flags & _lib.FLAG_ACCUM_RGBA8
-    eng, ora, stats = _render_both(rv, oracle_mod, prep, W, H, pose, flags=flags, oracle_flags=oflags, **kw)
-    if case == "rgba8":
-        assert np.array_equal(eng.read_accum_f32(), ora.accum_f32())
-    else:
-        _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"flow kernel, {case}")
-    assert np.array_equal(eng.read_output_rgba8(), ora.result)
-    st, active = stats[-1]
-    assert st["active"] == active
-    assert st["kernel_launches"] == kw.get("aa", 1)
-
-
-@pytest.mark.parametrize("size", [(1, 1), (7, 5), (17, 33), (640, 360)])
-def test_flow_kernel_sizes_and_partition(rv, oracle_mod, builtin, size):
-    """Ragged / tiny images (most CTAs never get a chunk) and a 3-way tile partition."""
-    from rvpt_b200 import _lib
-    W, H = size
-    eng, ora, _ = _render_both(rv, oracle_mod, builtin, W, H, DEFAULT_POSE, frames=2, flags=_lib.FLAG_FLOW,
-                               oracle_flags=0)
-    full = eng.read_accum_f32()
-    _assert_bit_equal(full, ora.accum, f"flow kernel {W}x{H}")
-    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
-    acc = np.zeros_like(full)
-    for r in range(3):
-        part = rv.Engine(W, H, flags=_lib.FLAG_FLOW, rank=r, nranks=3)
-        part.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
-        for f in range(2):
-            part.render_frame(rv.default_settings(frame=f), cam)
-        acc += part.read_accum_f32()
-    _assert_bit_equal(acc, full, "flow kernel, 3-way partition")
 
 
 def test_wave_forecast_is_scheduling_only(rv, oracle_mod, builtin):
@@ -641,3 +611,134 @@ def test_octant_sorted_queues_are_scheduling_only(rv, oracle_mod, cornell, unfus
         _assert_bit_equal(a.read_accum_f32(), ora.accum, f"sorted queues {W}x{H}")
         _assert_bit_equal(b.read_accum_f32(), ora.accum, f"single queue {W}x{H}")
         assert st_a[-1][0]["active"] == st_b[-1][0]["active"] == st_a[-1][1]
+
+
+# ---- batched launches: rvpt_b200_render_frames merges the waves of consecutive frames --------
+
+def _batched_vs_oracle(rv, oracle_mod, prep, W, H, pose, batches, flags=0, fov=90.0, rank=0, nranks=1,
+                       **settings_kw):
+    """Renders `batches` (a list of frame counts) with consecutive render_frames calls and the
+    same frames one by one with the oracle; returns (engine, oracle, per-launch oracle ray sums)."""
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    eng = rv.Engine(W, H, flags=flags, rank=rank, nranks=nranks)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes, flags=flags & 0x3)
+    frame = 0
+    for n in batches:
+        eng.render_frames(rv.default_settings(frame=frame, **settings_kw), cam, n)
+        st = eng.stats()
+        want = np.zeros(64, np.uint64)
+        for f in range(frame, frame + n):
+            ora.render_frame(rv.default_settings(frame=f, **settings_kw), cam)
+            if f >= frame + n - st["frames"]:
+                want += ora.active
+        if nranks == 1:
+            got = np.zeros(64, np.uint64)
+            got[:len(st["active"])] = st["active"]
+            assert np.array_equal(got, want), f"ray counts of the last launch ({st['frames']} frames)"
+            assert st["samples"] == int(want[0]) or settings_kw.get("max_bounces", 8) == 0
+        frame += n
+    return eng, ora
+
+
+@pytest.mark.parametrize("case", ["builtin_16", "pinned_5_11", "cornell_8_8", "cornell_rgba8", "dispatch",
+                                  "ortho", "spherical", "b1", "b2", "b16", "max_batch", "two_launches"])
+def test_batched_launch_bit_exact(rv, oracle_mod, builtin, cornell, case):
+    """A batch renders frames f..f+n-1 in ONE launch: primary rays of all frames in one wave,
+    bounce waves merged across frames, samples folded into the running mean in frame order by
+    the resolve phase. The images after the batch equal n render_frame calls / the oracle."""
+    from rvpt_b200 import _lib
+    kw = {}
+    if case == "builtin_16":
+        prep, W, H, pose, batches = builtin, 320, 180, DEFAULT_POSE, [16]
+    elif case == "pinned_5_11":
+        prep, W, H, pose, batches = builtin, 256, 256, PINNED_POSE, [5, 11, 1, 2]
+    elif case == "cornell_8_8":   # the second launch queues by octant (closed-scene forecast)
+        prep, W, H, pose, batches, kw = cornell, 200, 152, CORNELL_POSE, [8, 8], dict(fov=60.0)
+    elif case == "cornell_rgba8":
+        prep, W, H, pose, batches, kw = cornell, 160, 96, CORNELL_POSE, [6, 3], dict(
+            fov=60.0, flags=_lib.FLAG_ACCUM_RGBA8)
+    elif case == "dispatch":
+        prep, W, H, pose, batches, kw = builtin, 200, 90, PINNED_POSE, [4], dict(
+            flags=_lib.FLAG_REFERENCE_DISPATCH)
+    elif case == "ortho":
+        prep, W, H, pose, batches, kw = builtin, 128, 64, PINNED_POSE, [3], dict(camera_mode=1)
+    elif case == "spherical":
+        prep, W, H, pose, batches, kw = builtin, 128, 64, PINNED_POSE, [3], dict(camera_mode=2)
+    elif case in ("b1", "b2", "b16"):
+        prep, W, H, pose, batches, kw = cornell, 64, 48, CORNELL_POSE, [3, 2], dict(
+            fov=60.0, max_bounces=int(case[1:]))
+    elif case == "max_batch":
+        prep, W, H, pose, batches = builtin, 17, 33, DEFAULT_POSE, [64]
+    else:  # more frames than one launch can tag (64): split into equal launches
+        prep, W, H, pose, batches = builtin, 64, 48, PINNED_POSE, [70]
+    eng, ora = _batched_vs_oracle(rv, oracle_mod, prep, W, H, pose, batches, **kw)
+    if kw.get("flags", 0) & _lib.FLAG_ACCUM_RGBA8:
+        assert np.array_equal(eng.read_accum_f32(), ora.accum_f32())
+    else:
+        _assert_bit_equal(eng.read_accum_f32(), ora.accum, case)
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    if case == "two_launches":
+        assert eng.stats()["frames"] == 35
+
+
+def test_batched_launch_partition_and_large_scene(rv, oracle_mod, builtin):
+    """Batches on a 3-way tile partition (ragged image) reassemble the oracle's image; a scene on
+    the global-memory path batches too; NO_BATCH is the same computation frame by frame."""
+    from conftest import PreparedScene
+    from rvpt_b200 import _lib
+    W, H = 208, 120
+    acc = np.zeros((H, W, 4), np.float32)
+    for r in range(3):
+        eng, ora = _batched_vs_oracle(rv, oracle_mod, builtin, W, H, PINNED_POSE, [7], rank=r, nranks=3)
+        acc += eng.read_accum_f32()
+        eng.close()
+    _assert_bit_equal(acc, ora.accum, "3-way partition, batch of 7")
+    prep = PreparedScene(rv, rv.displaced_sphere_scene(20000))
+    eng, ora = _batched_vs_oracle(rv, oracle_mod, prep, 192, 128, (0.0, 1.2, -3.0), [4, 2], fov=60.0)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "global-memory path, batches of 4 and 2")
+    eng, ora = _batched_vs_oracle(rv, oracle_mod, builtin, 160, 96, DEFAULT_POSE, [5],
+                                  flags=_lib.FLAG_NO_BATCH)
+    assert eng.stats()["frames"] == 1
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "NO_BATCH")
+
+
+def test_batch_size_follows_the_queue_budget(rv, oracle_mod, builtin, monkeypatch):
+    """The path queues of a launch must fit RVPT_B200_QUEUE_BUDGET_MIB: 256x256 needs 64 MiB per
+    frame of a batch (8 octant sub-queues x 2 queues x 64 B), so 200 MiB allows 3 frames."""
+    monkeypatch.setenv("RVPT_B200_QUEUE_BUDGET_MIB", "200")
+    eng, ora = _batched_vs_oracle(rv, oracle_mod, builtin, 256, 256, DEFAULT_POSE, [7])
+    assert eng.stats()["frames"] == 1  # 7 frames -> launches of 3, 3, 1
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "budget-limited batches")
+
+
+@pytest.mark.parametrize("flags_name", ["batched", "frame_by_frame"])
+def test_cuda_graph_replay_is_safe_for_any_launch_count(rv, oracle_mod, builtin, flags_name):
+    """A CUDA graph captured through the C ABI replays correctly whatever number of launches it
+    holds (3 frame launches here, or one batched launch): no device state depends on host-side
+    launch parity — the last CTA of every launch leaves the counters clean (round-1 advice)."""
+    torch = pytest.importorskip("torch")
+    from rvpt_b200 import _lib
+    W, H, N = 320, 180, 3
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    rs = rv.default_settings(frame=0)
+    flags = 0 if flags_name == "batched" else _lib.FLAG_NO_BATCH
+    eng = rv.Engine(W, H, flags=flags)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    eng.render_frames(rs, cam, N)  # warm-up: allocations happen outside the capture
+    eng.sync()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            eng.render_frames(rs, cam, N)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+    for f in range(N):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+    for replay in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"graph replay {replay}")
+    eng.set_stream(None)
+    eng.close()
