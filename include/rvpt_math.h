@@ -32,6 +32,13 @@
 #define RV_TWO_PI 6.28318548202514648f  /* 0x40C90FDB */
 #define RV_INV_PI 0.318309873342514038f /* 0x3EA2F983 */
 #define RV_EPSILON 0.005f               /* 0x3BA3D70A */
+/* normalize(vec3(0.5, 1, 0.3)), the directional light of the Utah / Appel / Whitted integrators
+ * (integrators.glsl:121,218,274): glslang folded it at compile time in double precision, so the
+ * shipped compute_pass.comp.spv holds these three constants (%1585-%1587) — z is one ulp below
+ * what a float32 normalize returns (0x3E84B0B1). Found by running the binary (oracle/spirv_vm.cpp). */
+#define RV_LIGHT_DIR_X 0.431934207677841187f /* 0x3EDD267B */
+#define RV_LIGHT_DIR_Y 0.863868415355682373f /* 0x3F5D267B */
+#define RV_LIGHT_DIR_Z 0.259160518646240234f /* 0x3E84B0B0 */
 
 struct rv_f3
 {

@@ -6,13 +6,16 @@
  * from the GLSL. Only tests/, __graft_entry__.smoke() and bench.py's CPU
  * baseline legs may load this library; nothing under rvpt_b200/ does.
  *
- * PARITY UNPINNED: the reference ships no tests, golden images or known-answer
- * vectors for this path, and it cannot be built or run here (no Vulkan loader,
- * ICD, glslang, glm, GLFW; its own BVH builder aborts on the built-in scene —
- * SURVEY.md §2.2, §8c). The only specification is the GLSL source; the pins
- * this oracle is checked against (tests/test_oracle_kats.py) are KATs derived
- * from that source: wang_hash / xorshift values, struct layouts from the shipped
- * SPIR-V decorations, constant bit patterns.
+ * PARITY PINNED to the reference's own shipped build of this path: the repo holds no tests,
+ * golden images or known-answer vectors, and its Vulkan path cannot run here (no loader / ICD),
+ * but it ships the shader COMPILED — assets/shaders/compute_pass.comp.spv. oracle/spirv_vm.cpp
+ * executes that binary with the reference's bindings; this oracle equals its output bit for bit
+ * on every case of tests/golden/make_spirv_golden.py (all configs' shapes, both image formats,
+ * every integrator and camera; live in tests/test_spirv_pin.py next to the reference,
+ * through committed digests elsewhere). That run found one deviation in round 2 — glslang had
+ * folded normalize(vec3(0.5,1,0.3)) in double precision (RV_LIGHT_DIR_* in rvpt_math.h).
+ * What stays unpinned is what SPIR-V itself leaves to the Vulkan driver: summation order of
+ * dot / mat*vec, accuracy of sin / cos / tan / normalize, UNORM8 rounding (next paragraph).
  *
  * Driver-defined float behaviour (summation order of dot/cross/normalize/mix/
  * mat*vec, sin/cos/tan) is fixed by include/rvpt_math.h; GLSL min/max on NaN is
@@ -548,8 +551,9 @@ rv_f3 integrator_Kajiya(const Scene& sc, Ray primary_ray, float mint, float maxt
 
 rv_f3 splat(float v) { return rv_make(v, v, v); }
 
-/* the directional light of the Utah / Appel / Whitted models: normalize(vec3(0.5,1,0.3)) */
-rv_f3 light_direction() { return rv_normalize(rv_make(0.5f, 1.0f, 0.3f)); }
+/* the directional light of the Utah / Appel / Whitted models: normalize(vec3(0.5,1,0.3)) as the
+ * shipped SPIR-V holds it (constant-folded by glslang; see RV_LIGHT_DIR_* in rvpt_math.h) */
+rv_f3 light_direction() { return rv_make(RV_LIGHT_DIR_X, RV_LIGHT_DIR_Y, RV_LIGHT_DIR_Z); }
 
 /* integrators.glsl:24-38 */
 rv_f3 integrator_binary(const Scene& sc, const Ray& ray, float mint, float maxt, Counters* ctr)

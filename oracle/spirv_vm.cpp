@@ -406,8 +406,8 @@ struct Machine
             for (uint32_t k = 0; k < n; ++k)
             {
                 const double a = asd(x + 2 * k), b = asd(y + 2 * k);
-                /* FMin: y < x ? y : x ; FMax: x < y ? y : x (GLSL.std.450 definitions) */
-                putd(r + 2 * k, inst == 37 ? (b < a ? b : a) : (a < b ? b : a));
+                /* NaN operands are undefined in GLSL.std.450; resolved as IEEE minNum/maxNum like the f32 case */
+                putd(r + 2 * k, inst == 37 ? fmin(a, b) : fmax(a, b));
             }
             return true;
         }
@@ -429,7 +429,7 @@ struct Machine
             {
                 const uint32_t* y = V(frame, ops[1]);
                 for (uint32_t k = 0; k < n; ++k)
-                    r[k] = asu(inst == 37 ? rv_min(asf(x[k]), asf(y[k])) : rv_max(asf(x[k]), asf(y[k])));
+                    r[k] = asu(inst == 37 ? fminf(asf(x[k]), asf(y[k])) : fmaxf(asf(x[k]), asf(y[k])));
                 return true;
             }
             case 38:
@@ -441,7 +441,7 @@ struct Machine
             case 43: /* FClamp = min(max(x, lo), hi) */
             {
                 const uint32_t *lo = V(frame, ops[1]), *hi = V(frame, ops[2]);
-                for (uint32_t k = 0; k < n; ++k) r[k] = asu(rv_min(rv_max(asf(x[k]), asf(lo[k])), asf(hi[k])));
+                for (uint32_t k = 0; k < n; ++k) r[k] = asu(fminf(fmaxf(asf(x[k]), asf(lo[k])), asf(hi[k])));
                 return true;
             }
             case 46: /* FMix = x*(1-a) + y*a */

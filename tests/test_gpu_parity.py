@@ -159,6 +159,37 @@ def test_gpu_matches_committed_golden_pins(rv, oracle_mod, builtin, cornell):
         eng.close()
 
 
+def test_gpu_reproduces_spirv_pins(rv):
+    """The CUDA path against the reference's SHIPPED shader binary: tests/golden/spirv_pins.json
+    holds digests of what assets/shaders/compute_pass.comp.spv computes (executed by
+    oracle/spirv_vm.cpp; generated by tests/golden/make_spirv_golden.py next to the reference).
+    Float32 running mean bit for bit and rgba8 codes, every case: C1 both poses, the reference's
+    own UNORM8 + W/16 dispatch configuration, a 1080p band, Cornell, aa, bounce limits, cameras,
+    integrators 0-8, split view."""
+    import json
+    from golden import make_spirv_golden as G
+    pins = json.loads(G.PINS.read_text())
+    prepared = {}
+    for name, s in G.scenes(rv).items():
+        nodes, perm = rv.build_bvh(s.triangles)
+        prepared[name] = (nodes, np.ascontiguousarray(s.triangles[perm]), s.materials)
+    for name, c in G.CASES.items():
+        nodes, tris, mats = prepared[c["scene"]]
+        flags = (1 if c["unorm8"] else 0) | (2 if c["ref_dispatch"] else 0)
+        eng = rv.Engine(c["W"], c["H"], flags=flags)
+        eng.upload_scene(tris, mats, nodes)
+        cam = rv.camera_data(translation=c["pose"], aspect=c["W"] / c["H"], fov=c["fov"])
+        for f in range(c["frames"]):
+            eng.render_frame(G.settings_for(rv, c, f), cam)
+        got = G.digests(c, eng.read_accum_f32(), eng.read_output_rgba8())
+        for key in ("temporal", "rgba8"):
+            if got[key]["sha256"] != pins[name][key]["sha256"]:
+                rows = [i for i, (a, b) in enumerate(zip(got[key]["rows_crc32"], pins[name][key]["rows_crc32"]))
+                        if a != b]
+                raise AssertionError(f"{name}/{key}: {len(rows)} rows differ from the SPIR-V run, first {rows[:8]}")
+        eng.close()
+
+
 @pytest.mark.parametrize("aa", [1, 2])
 def test_multi_frame_launch_equals_frame_by_frame(rv, oracle_mod, cornell, aa):
     """rvpt_b200_render_frames(n) == n x render_frame with current_frame++ ==
