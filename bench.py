@@ -4,35 +4,42 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): built-in scene (143-triangle bunny,
-white Lambert, procedural sky; src/rvpt/main.cpp:102-107), literal default
-camera, 1920x1080, max_bounces 8, aa 1, progressive accumulation. One STEP is a
-progressive batch of `--frames` frames (default 16 spp): frame counter 0..F-1,
-so every step restarts the running mean (compute_pass.comp:146-148 multiplies
-the previous image by min(frame,1)).
+Workload (BASELINE.json configs[1], "C2"; SURVEY.md 8(d)): built-in scene (143-triangle bunny,
+white Lambert, procedural sky; src/rvpt/main.cpp:102-107), literal default camera, 1920x1080,
+max_bounces 8, aa 1, progressive accumulation. One STEP is the progressive batch of 8(d):
+frames 0..63 (`--frames`), through ONE C-ABI call, rvpt_b200_render_frames — every step restarts
+the running mean (compute_pass.comp:146-148 multiplies the previous image by min(frame, 1)).
+The workload's bytes (BVH, triangles, materials, camera) are committed under oracle/workloads/.
 
-  value  device-resident throughput: scene uploaded once, frames launched back
-         to back through the C ABI, CUDA events on the launch stream.
-  e2e    the same step through the host-buffer API: upload_scene from host
-         arrays, F x render_frame (settings + camera by value), read back the
-         rgba8 result into pinned host memory — all inside the timed region.
+  value   device-resident throughput: scene uploaded once, CUDA events on the launch stream
+          around each step, 256 MiB memset between steps (L2 flush, outside the events).
+  e2e     the same step through the host-buffer API: upload_scene from host arrays + the
+          render_frames call (settings + camera by value) + read_output_rgba8 into pinned host
+          memory — all inside the timed region, wall clock.
+  parity_ok  the rgba8 image the last timed step left behind == the CPU oracle's image of the
+          same 64 frames, byte for byte (at every N: the image rank 0 assembled).
+  c4      secondary record: BASELINE.json configs[3], 3840x2160 x 16 progressive frames, same
+          timing discipline and the same parity check.
 
-N > 1 (one process per GPU, NCCL): the frame is sharded by 16x16 pixel tile
-(tile_id % N == rank), every rank renders its tiles, and ONE all-gather of the
-rgba8 tiles per frame assembles the image on every rank (in place: the kernels
-write straight into the rank's slot of the gather buffer). Total work is fixed
-("scaling": "strong").
+N > 1 (one process per GPU): the frame is sharded by 16x16 pixel tile (tile_id % N == rank);
+every rank renders its tiles, nothing is exchanged while rendering. Assembly on rank 0:
+  p2p (default)  the kernels' resolve phase stores finished rgba8 pixels straight into rank 0's
+                 raster image over NVLink peer memory (CUDA IPC) — fused, no collective; NCCL
+                 carries the rendezvous and one barrier per step;
+  nccl           the kernels write tiles into the rank's slot of a gather buffer, ONE
+                 all_gather_into_tensor per step, untile on rank 0.
+Total work is fixed ("scaling": "strong").
 
---impl reference times the CPU restatement of the reference shader
-(oracle/rvpt_oracle.cpp — the reference's Vulkan path cannot run here, see
-DESIGN.md) with all host threads on a bounded sample of the same workload.
+--impl reference times the CPU restatement of the reference shader (oracle/rvpt_oracle.cpp; the
+reference's Vulkan path cannot run here) with all host threads, one full frame of the
+same workload per step. That arm loads only oracle/ — never the product library.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -47,91 +54,99 @@ METRIC = "Msamples/s at 1920x1080, 8-bounce, built-in scene"
 UNIT = "Msamples/s"
 
 
-
 def measured_hbm_peak():
-    """HBM roofline denominator: the driver-written MEASURED_PEAKS.json when present (the kernel is
-    timed inside a long step, so a sustained figure is preferred over a burst one when the file
-    distinguishes them), else the fallback of /opt/skills/guides/B200_PROFILING.md."""
-    path = ROOT / "MEASURED_PEAKS.json"
+    """HBM roofline denominator: the driver-written MEASURED_PEAKS.json when present, else the
+    fallback of /opt/skills/guides/B200_PROFILING.md."""
     try:
-        peaks = json.loads(path.read_text())
-        flat = {}
-
-        def walk(prefix, obj):
-            if isinstance(obj, dict):
-                for k, v in obj.items():
-                    walk(f"{prefix}.{k}" if prefix else str(k), v)
-            elif isinstance(obj, (int, float)):
-                flat[prefix.lower()] = float(obj)
-
-        walk("", peaks)
-        if flat.get("hbm_gbs", 0.0) > 0.0:
-            return flat["hbm_gbs"], "measured"
-        hbm = {k: v for k, v in flat.items() if "hbm" in k and v > 100.0}
-        for pick in (lambda k: "sustain" in k, lambda k: "burst" not in k, lambda k: True):
-            for k, v in hbm.items():
-                if pick(k):
-                    return v, "measured"
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        if float(peaks.get("hbm_gbs", 0.0)) > 0.0:
+            return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except (OSError, ValueError):
         pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--frames", type=int, default=16, help="progressive frames (spp) per step")
+    ap.add_argument("--frames", type=int, default=64, help="progressive frames per step (SURVEY 8(d): 64)")
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--aa", type=int, default=1)
-    ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell", "mesh"])
+    ap.add_argument("--scene", default="builtin", choices=["builtin", "cornell", "mesh", "tridel"])
     ap.add_argument("--mesh-tris", type=int, default=500000)
     ap.add_argument("--pose", default="default", choices=["default", "pinned"])
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
-                    help="N>1: p2p = kernels store pixels into rank 0's image over NVLink (fused); "
-                         "nccl = one all_gather_into_tensor per frame + untile")
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the last step")
+    ap.add_argument("--no-c4", action="store_true", help="skip the secondary 3840x2160 x16 record")
     ap.add_argument("--frame-by-frame", action="store_true",
                     help="one rvpt_b200_render_frame call (= one launch) per frame instead of one "
                          "rvpt_b200_render_frames batch per step")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+    ap.add_argument("--graph", default="off", choices=["on", "off"],
                     help="replay each step from a CUDA graph (captured through the C ABI)")
     return ap.parse_args()
 
 
-def workload(args):
+def workload_name(args) -> str:
+    if args.scene in ("builtin", "cornell"):
+        return f"{args.scene}_{args.pose if args.scene == 'builtin' else 'default'}"
+    return args.scene
+
+
+def describe(args, n_tris, n_nodes, W, H, frames) -> str:
+    cfg = {"builtin": "C2", "cornell": "C3"}.get(args.scene, "f-1")
+    if (W, H) == (3840, 2160):
+        cfg = "C4"
+    return (f"{cfg}: {args.scene} scene ({n_tris} triangles, {n_nodes} BVH nodes), {args.pose} pose, "
+            f"{W}x{H}, max_bounces {args.bounces}, aa {args.aa}, progressive frames 0..{frames - 1}")
+
+
+def committed_workload(args):
+    """nodes, triangles (BVH order), materials, camera for the 16:9 configurations — from
+    oracle/workloads/ (no product code involved). None for generated scenes."""
+    import oracle
+    name = workload_name(args)
+    if not (ROOT / "oracle" / "workloads" / f"{name}.npz").exists():
+        return None
+    if abs(args.width / args.height - 16 / 9) > 1e-9:
+        return None
+    w = oracle.load_workload(name)
+    return w["nodes"], w["triangles"], w["materials"], w["camera_16x9"]
+
+
+def product_workload(args):
+    """The same arrays built at run time with the product's host helpers (GPU arm)."""
     import rvpt_b200 as rv
     if args.scene == "builtin":
         scene = rv.builtin_scene()
-        pose = (0.0, 0.0, 0.0) if args.pose == "default" else (0.0, 0.8, -2.5)
-        fov = 90.0
+        pose, fov = ((0.0, 0.0, 0.0) if args.pose == "default" else (0.0, 0.8, -2.5)), 90.0
     elif args.scene == "mesh":
         scene = rv.displaced_sphere_scene(args.mesh_tris)
         pose, fov = (0.0, 1.2, -3.0), 60.0
+    elif args.scene == "tridel":
+        from rvpt_b200.scene import tridel_scene
+        scene, pose, fov = tridel_scene()
     else:
         scene = rv.cornell_scene()
         pose, fov = (0.0, 1.2, -3.4), 60.0
     nodes, perm = rv.build_bvh(scene.triangles)
     tris = np.ascontiguousarray(scene.triangles[perm])
     cam = rv.camera_data(translation=pose, aspect=args.width / args.height, fov=fov)
-    name = (f"C2 {args.scene} scene ({len(tris)} triangles, {len(nodes)} BVH nodes), "
-            f"{args.pose} pose, {args.width}x{args.height}, max_bounces {args.bounces}, aa {args.aa}")
-    return rv, scene, nodes, tris, cam, name
+    return nodes, tris, scene.materials, cam
 
 
 class ClockSampler:
-    """SM clocks and throttle reasons DURING the timed region. Polls NVML (the
-    library behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,
-    clocks_event_reasons.*`) every 2 ms from a thread between start() and stop()."""
+    """SM clocks and throttle reasons DURING the timed region. Polls NVML (the library behind
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`) every 2 ms from a
+    thread between start() and stop()."""
 
-    REASONS = {  # nvmlClocksEventReason* bits -> the nvidia-smi field names
-        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
-        0x4: "sw_power_cap",
-    }
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
@@ -184,50 +199,35 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_rate(args, nodes, tris, mats, cam, seconds: float, nthreads: int = 0):
-    """Times the CPU oracle on a bounded sample of the workload: a centred band
-    of rows of frame 0.., grown until ~`seconds` of work. Returns (Msamples/s,
-    cores, description)."""
+def oracle_frames(W, H, nodes, tris, mats, cam, frames, bounces, aa, nthreads=0):
+    """Renders frames 0..frames-1 with the CPU oracle. Returns (rgba8 image, seconds, cores)."""
     import oracle
-    rvsettings = __import__("rvpt_b200").default_settings
-    W, H = args.width, args.height
     ora = oracle.OracleRenderer(W, H, tris, mats, nodes, nthreads=nthreads)
     cores = nthreads or oracle.load().rvpt_oracle_hardware_threads()
-    # calibrate on 64 centred rows
-    y0 = max(0, H // 2 - 32)
-    y1 = min(H, y0 + 64)
-    t = time.perf_counter()
-    ora.render_frame(rvsettings(max_bounces=args.bounces, aa=args.aa, frame=0), cam, y0, y1)
-    dt = time.perf_counter() - t
-    rate = (y1 - y0) * W * args.aa / dt
-    # bounded sample: whole frames, as many as fit the budget (at least one)
-    frames = int(max(1, min(64, seconds * rate / (W * H * args.aa))))
-    ora = oracle.OracleRenderer(W, H, tris, mats, nodes, nthreads=nthreads)
     t = time.perf_counter()
     for f in range(frames):
-        ora.render_frame(rvsettings(max_bounces=args.bounces, aa=args.aa, frame=f), cam)
-    dt = time.perf_counter() - t
-    msps = frames * W * H * args.aa / dt / 1e6
-    return msps, cores, f"{frames} full frame(s) of the workload, {dt:.1f} s on {cores} threads"
+        ora.render_frame(oracle.settings(max_bounces=bounces, aa=aa, frame=f), cam)
+    return ora.result, time.perf_counter() - t, cores
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference shader on the box's
-    host cores (kind "port": the Vulkan path cannot be built here)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """Reference arm: the CPU restatement of the reference shader on the box's host cores (kind
+    "port": the Vulkan path cannot be built here). Loads oracle/ only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    rv, scene, nodes, tris, cam, name = workload(args)
     import oracle
+    wl = committed_workload(args)
+    if wl is None:  # generated scenes have no committed copy: build them with the host helpers
+        wl = product_workload(args)
+    nodes, tris, mats, cam = wl
     W, H = args.width, args.height
     cores = oracle.load().rvpt_oracle_hardware_threads()
-    ora = oracle.OracleRenderer(W, H, tris, scene.materials, nodes)
-    # one step = one full frame of the workload (bounded sample of the 16-frame step)
+    ora = oracle.OracleRenderer(W, H, tris, mats, nodes)
     frame = 0
 
-    def step():
+    def step():  # one full frame of the workload (a bounded sample of the 64-frame step)
         nonlocal frame
-        ora.render_frame(rv.default_settings(max_bounces=args.bounces, aa=args.aa, frame=frame), cam)
+        ora.render_frame(oracle.settings(max_bounces=args.bounces, aa=args.aa, frame=frame % args.frames), cam)
         frame += 1
 
     for _ in range(args.warmup):
@@ -237,17 +237,132 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t
     msps = args.steps * W * H * args.aa / dt / 1e6
-    sample = f"each step = 1 full frame ({W}x{H}x{args.aa} samples) of the workload"
+    sample = (f"each step = 1 full frame ({W}x{H}x{args.aa} samples) of the workload's {args.frames}-frame "
+              f"progressive batch, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": msps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": name, "sample": sample},
-        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": {"workload": describe(args, len(tris), len(nodes), W, H, args.frames),
+                   "frames_per_step": args.frames},
+        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+class Runner:
+    """One engine + the per-step plumbing of one configuration (resolution, frames per step)."""
+
+    def __init__(self, args, torch, dist, rv, wl, W, H, F, rank, world, local_rank, stream):
+        self.args, self.torch, self.dist, self.rv = args, torch, dist, rv
+        self.W, self.H, self.F, self.rank, self.world = W, H, F, rank, world
+        self.nodes, self.tris, self.mats, self.cam = wl
+        self.eng = rv.Engine(W, H, device=local_rank, rank=rank, nranks=world)
+        self.eng.set_stream(stream.cuda_stream)
+        self.eng.upload_scene(self.tris, self.mats, self.nodes)
+        self.settings = [rv.default_settings(max_bounces=args.bounces, aa=args.aa, frame=f) for f in range(F)]
+        self.settings_ptr = [s.ctypes.data for s in self.settings]
+        self.cam_ptr = self.cam.ctypes.data
+        self.fg = self.po = None
+        self.gather = args.gather if world > 1 else "none"
+        dev = torch.device("cuda", local_rank)
+        if self.gather == "nccl":
+            from rvpt_b200.distributed import FrameGather
+            self.fg = FrameGather(self.eng, dist, torch, dev)
+        elif self.gather == "p2p":
+            from rvpt_b200.distributed import PeerOutput
+            self.po = PeerOutput(self.eng, dist, torch, dev)
+        self.out_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+        self.out_np = self.out_pinned.numpy()
+
+    def frames_of_step(self):
+        if self.fg:
+            self.fg.begin_frame()  # device-side wait for the buffer's previous gather
+        if self.args.frame_by_frame:
+            for f in range(self.F):
+                self.eng.render_frame_raw(self.settings_ptr[f], self.cam_ptr)
+        else:
+            self.eng.render_frame_raw(self.settings_ptr[0], self.cam_ptr, self.F)
+        if self.fg:
+            self.fg.end_frame()    # ONE all-gather for the step's image + untile on rank 0
+            self.fg.flush()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def read_image(self):
+        """The step's assembled rgba8 image on rank 0 (device -> pinned host)."""
+        if self.world == 1:
+            self.eng.read_output_rgba8(self.out_np)
+        elif self.po:
+            self.po.finish()       # every rank's pixels have landed in rank 0's image
+            if self.rank == 0:
+                self.eng.read_output_rgba8(self.out_np)
+        elif self.fg:
+            if self.rank == 0:
+                self.out_pinned.view(self.torch.int32).view(-1).copy_(self.fg.raster, non_blocking=False)
+            else:
+                self.torch.cuda.synchronize()
+        else:
+            self.torch.cuda.synchronize()
+        return self.out_np
+
+    def e2e_step(self):
+        self.eng.upload_scene(self.tris, self.mats, self.nodes)  # host arrays -> device, every step
+        self.frames_of_step()
+        self.read_image()
+
+    def time_steps(self, steps, warmup, stream, flush, graph):
+        """Device-timed steps: returns (total ms as max over ranks, launches per step, stats)."""
+        torch, dist = self.torch, self.dist
+        for _ in range(max(warmup, 3)):
+            self.frames_of_step()
+        self.barrier()
+        step_graph, note = None, "direct launches"
+        if graph == "on" and self.gather != "nccl":
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                self.frames_of_step()
+            step_graph, note = g, "one CUDA graph per step (captured through the C ABI)"
+            step_graph.replay()
+            self.barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()
+        for k in range(steps):
+            flush.zero_()          # evict the accumulation image and the queues from L2 between steps
+            if self.world > 1:
+                dist.barrier()
+            starts[k].record(stream)
+            if step_graph is not None:
+                step_graph.replay()
+            else:
+                self.frames_of_step()
+            ends[k].record(stream)
+        self.barrier()
+        total = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64,
+                             device="cuda")
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()), note
+
+    def parity(self):
+        """The image of the last step (already rendered) against the oracle's frames 0..F-1."""
+        img = self.read_image()
+        ok = None
+        if self.rank == 0:
+            want, secs, cores = oracle_frames(self.W, self.H, self.nodes, self.tris, self.mats, self.cam,
+                                              self.F, self.args.bounces, self.args.aa)
+            ok = bool(np.array_equal(img, want))
+            self.oracle_run = (secs, cores)
+            self.image_sha256 = hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
+            self.diff_pixels = int((img != want).any(axis=-1).sum())
+        if self.world > 1:
+            self.dist.barrier()
+        return ok
 
 
 def run_ours(args):
@@ -257,215 +372,141 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    rv, scene, nodes, tris, cam, name = workload(args)
+    import rvpt_b200 as rv
+    wl = product_workload(args)
+    committed = committed_workload(args)
+    if committed is not None:  # both arms and the parity check see the same bytes
+        for a, b in zip(wl, committed):
+            assert np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes(), \
+                "oracle/workloads is stale: run tools/make_bench_workloads.py"
+    nodes, tris, mats, cam = wl
     W, H, F = args.width, args.height, args.frames
-    eng = rv.Engine(W, H, device=local_rank, rank=rank, nranks=world)
-    # a real (non-default) stream shared by torch and the engine, so torch's CUDA
-    # events bracket exactly the kernels the C ABI launches
+    # a real (non-default) stream shared by torch and the engine, so torch's CUDA events bracket
+    # exactly the kernels the C ABI launches
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    eng.set_stream(stream.cuda_stream)
-    eng.upload_scene(tris, scene.materials, nodes)
-
-    settings = [rv.default_settings(max_bounces=args.bounces, aa=args.aa, frame=f) for f in range(F)]
-    settings_ptr = [s.ctypes.data for s in settings]
-    cam_ptr = cam.ctypes.data
-
-    # multi-GPU assembly of the image on rank 0:
-    #   p2p   every rank's kernels store finished rgba8 pixels straight into rank 0's raster
-    #         image over NVLink (CUDA IPC peer mapping) — the gather is fused into the frame
-    #         kernel, nothing else runs per frame;
-    #   nccl  the kernels write tiles into the rank's slot of a gather buffer, ONE
-    #         all_gather_into_tensor per frame, rank 0 untiles.
-    fg = po = None
-    gather = args.gather if world > 1 else "none"
-    if gather == "nccl":
-        from rvpt_b200.distributed import FrameGather
-        fg = FrameGather(eng, dist, torch, torch.device("cuda", local_rank))
-    elif gather == "p2p":
-        from rvpt_b200.distributed import PeerOutput
-        po = PeerOutput(eng, dist, torch, torch.device("cuda", local_rank))
-
-    def frames_of_step():
-        if not fg and not args.frame_by_frame:
-            # the progressive batch through one C-ABI call (rvpt_b200_render_frames): frames 0..F-1
-            eng.render_frame_raw(settings_ptr[0], cam_ptr, F)
-            return
-        for f in range(F):
-            if fg:
-                fg.begin_frame()          # device-side wait for the buffer's previous gather
-            eng.render_frame_raw(settings_ptr[f], cam_ptr)
-            if fg:
-                fg.end_frame()            # async all-gather + untile
-        if fg:
-            fg.flush()                    # the step ends when its last image is assembled
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # 2x L2
 
-    # One step = F frame launches (+ F gathers). Captured once into a CUDA graph through
-    # the very same C-ABI calls and replayed: the host submits one graph per step
-    # instead of F cooperative launches + F collectives.
-    step_graph = None
-    graph_note = "off"
+    run = Runner(args, torch, dist, rv, wl, W, H, F, rank, world, local_rank, stream)
+    eng = run.eng
 
-    def run_step():
-        if step_graph is not None:
-            step_graph.replay()
-        else:
-            frames_of_step()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput ------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        frames_of_step()
-    barrier()
-    if args.graph != "off" and gather != "nccl":  # NCCL capture + side streams: not replay-safe here
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                frames_of_step()
-            step_graph, graph_note = g, "one CUDA graph per step (captured through the C ABI)"
-        except Exception as exc:  # noqa: BLE001
-            if args.graph == "on":
-                raise
-            graph_note = f"capture failed ({type(exc).__name__}): direct launches"
-            torch.cuda.synchronize()
-        ok = torch.tensor([1 if step_graph is not None else 0], device="cuda")
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            step_graph = None
-        for _ in range(2):
-            run_step()
-        barrier()
+    # ---- device-resident throughput --------------------------------------------------------
     sampler = ClockSampler(local_rank)
+    # warm-up + graph capture happen inside time_steps before its timed loop; the sampler is
+    # started right before and only keeps what it saw under load (median)
     if rank == 0:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        flush.zero_()              # evict the accumulation image from L2 between steps
-        if world > 1:
-            dist.barrier()
-        starts[k].record(stream)
-        run_step()
-        ends[k].record(stream)
-    barrier()
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    st = eng.stats()
-    launches_per_step = F * (st["kernel_launches"] + (1 if (fg and rank == 0) else 0))
+    total_ms, launch_note = run.time_steps(args.steps, args.warmup, stream, flush, args.graph)
     clocks = sampler.stop() if rank == 0 else None
-
+    st = eng.stats()                       # counters of the last launch (st["frames"] frames)
+    launches_per_step = st["kernel_launches"] + (1 if (run.fg and rank == 0) else 0)
     samples_per_step = W * H * args.aa * F
     value = args.steps * samples_per_step / (total_ms * 1e-3) / 1e6
 
-    # ---- per-kernel timing for the roofline (separate pass, same workload) --------------
+    # ---- parity of what was just timed -------------------------------------------------------
+    parity_ok = None if args.no_parity else run.parity()
+
+    # ---- roofline of the dominant kernel (separate pass, CUDA events around every launch) -----
     eng.set_profiling(True)
     eng.kernel_times()
-    for _ in range(2):
+    for _ in range(3):
         flush.zero_()
-        for f in range(F):
-            eng.render_frame_raw(settings_ptr[f], cam_ptr)   # frame by frame: one launch each
+        run.frames_of_step()
     kt = eng.kernel_times()
     eng.set_profiling(False)
     active = st["active"] + [0] * 64
-    S_local = st["samples"]
+    n_f = max(st["frames"], 1)             # frames the last launch covered
+    S = st["samples"]                      # samples of that launch (this rank)
     R = sum(active)
-    # DESIGN.md "algorithmic bytes": a terminated sample reads + writes the float4 running
-    # mean and writes rgba8 (36 B); every segment after the first writes and re-reads the
-    # 64 B path state (128 B). SURVEY 8(d)'s 128R + 36S additionally charges the primary
-    # ray a state round trip that the fused generation + bounce-0 wave never makes.
-    frame_bytes = 36 * S_local + 128 * (R - S_local)
-    survey_bytes = 128 * R + 36 * S_local
+    P = S // (n_f * args.aa) if n_f else 0  # pixels of this rank
+    # DESIGN.md "algorithmic bytes": every segment after the first writes and re-reads the 64 B
+    # path state (128 B). Batched launch (n_f > 1): a finished sample is parked (16 B written,
+    # 16 B read back by the resolve phase) and each pixel's running mean + rgba8 pixel move once
+    # per launch (36 B). Frame-by-frame launch: 36 B per sample.
+    if n_f > 1:
+        launch_bytes = 32 * S + 36 * P + 128 * (R - S)
+    else:
+        launch_bytes = 36 * S + 128 * (R - S)
+    survey_bytes = 128 * R + 36 * S        # SURVEY 8(d) literal formula (generate/trace unfused)
     kernel_ms = kt["primary_ms"] / max(kt["primary_launches"], 1)
     peak, peak_src = measured_hbm_peak()
-    achieved = frame_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    frame_ms = total_ms / (args.steps * F)
-    # dram__bytes_read.sum + dram__bytes_write.sum per k_frame launch from the committed
-    # `ncu --set full` capture of this command (profiles/), valid for the default workload only
+    achieved = launch_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic = None
     tpath = ROOT / "profiles" / "k_frame_traffic.json"
-    default_wl = (args.scene, args.pose, W, H, args.bounces, args.aa, world) == \
-        ("builtin", "default", 1920, 1080, 8, 1, 1)
+    default_wl = (args.scene, args.pose, W, H, args.bounces, args.aa, world, F, args.frame_by_frame) == \
+        ("builtin", "default", 1920, 1080, 8, 1, 1, 64, False)
     if tpath.exists() and default_wl:
-        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+        tj = json.loads(tpath.read_text())
+        if tj.get("frames_per_launch") == n_f:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": "k_frame (one persistent cooperative launch per frame: primary "
-                                  "wave + bounce waves + in-place accumulation)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": traffic,
-        "bytes_per_launch": frame_bytes, "ms_per_launch": kernel_ms,
+        "bound": "hbm",
+        "kernel": f"k_frame<batched> (one persistent cooperative launch per {n_f} frames: merged primary + "
+                  "bounce waves, parked samples, in-order resolve)" if n_f > 1 else
+                  "k_frame (one persistent cooperative launch per frame)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": traffic, "bytes_per_launch": launch_bytes, "ms_per_launch": kernel_ms,
+        "frames_per_launch": n_f, "launches_timed": kt["primary_launches"],
         "survey_8d_formula_bytes": survey_bytes,
         "survey_8d_formula_gbs": survey_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
-        "frame_ms_in_timed_region": frame_ms,
-        "rays_per_sample": R / max(S_local, 1), "active_per_bounce": st["active"],
-        "note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md); inside a step the "
-                "41.5 MB accumulation working set is L2-resident (126 MB L2); L2 is flushed "
-                "between steps",
+        "rays_per_sample": R / max(S, 1), "active_per_bounce_last_launch": st["active"],
+        "note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md section 4); L2 is flushed between steps",
     }
 
-    # ---- end to end through the host-buffer API -----------------------------------------
-    out_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
-    out_np = out_pinned.numpy()
-    mats = scene.materials
-    scene_h2d = nodes.nbytes + tris.nbytes + mats.nbytes
-    h2d = scene_h2d + F * (40 + 80)
+    # ---- end to end through the host-buffer API ------------------------------------------------
+    h2d = nodes.nbytes + tris.nbytes + mats.nbytes + 40 + 80
     d2h = W * H * 4
-
-    def e2e_step():
-        eng.upload_scene(tris, mats, nodes)           # host arrays -> device, every step
-        frames_of_step()
-        if world == 1:
-            eng.read_output_rgba8(out_np)              # device -> pinned host, synchronises
-        elif po:
-            po.finish()                                # all ranks' pixels are in rank 0's image
-            if rank == 0:
-                eng.read_output_rgba8(out_np)
-        elif fg:
-            if rank == 0:
-                out_pinned.view(torch.int32).view(-1).copy_(fg.raster, non_blocking=False)
-            else:
-                torch.cuda.synchronize()
-        else:
-            torch.cuda.synchronize()
-
     for _ in range(3):
-        e2e_step()
-    barrier()
+        run.e2e_step()
+    run.barrier()
     e2e_steps = max(5, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
+        run.e2e_step()
+    run.barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps * samples_per_step / float(e2e_s.item()) / 1e6
 
-    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle run of the parity check, timed ----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        msps, cores, sample = oracle_rate(args, nodes, tris, mats, cam, args.cpu_baseline_seconds)
-        cpu = {"value": msps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if getattr(run, "oracle_run", None) is None:
+            _, secs, cores = oracle_frames(W, H, nodes, tris, mats, cam, min(F, 16), args.bounces, args.aa)
+            n_frames = min(F, 16)
+        else:
+            (secs, cores), n_frames = run.oracle_run, F
+        cpu = {"value": n_frames * W * H * args.aa / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_frames} full frames of the workload (the oracle run of the parity check), "
+                         f"{secs:.1f} s on {cores} threads"}
+
+    # ---- secondary record: C4, 3840x2160 x 16 progressive frames --------------------------------
+    c4 = None
+    if not args.no_c4 and args.scene == "builtin" and (W, H) == (1920, 1080):
+        run.eng.close()
+        c4_args = argparse.Namespace(**vars(args))
+        c4_args.width, c4_args.height, c4_args.frames = 3840, 2160, 16
+        r4 = Runner(c4_args, torch, dist, rv, wl, 3840, 2160, 16, rank, world, local_rank, stream)
+        ms4, _ = r4.time_steps(max(5, args.steps // 2), args.warmup, stream, flush, "off")
+        steps4 = max(5, args.steps // 2)
+        ok4 = None if args.no_parity else r4.parity()
+        st4 = r4.eng.stats()
+        if rank == 0:
+            c4 = {"workload": describe(c4_args, len(tris), len(nodes), 3840, 2160, 16),
+                  "value": steps4 * 3840 * 2160 * 16 * args.aa / (ms4 * 1e-3) / 1e6, "unit": UNIT,
+                  "ms_per_step": ms4 / steps4, "steps": steps4, "frames_per_step": 16,
+                  "launches_per_step": st4["kernel_launches"], "parity_ok": ok4}
+        r4.eng.close()
 
     if rank == 0:
         line = {
@@ -473,23 +514,30 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": name, "frames_per_step": F, "samples_per_step": samples_per_step,
-                       "partition": f"16x16 tiles, tile_id % {world} == rank" if world > 1 else "none",
-                       "gather": {"p2p": "fused: kernels store rgba8 pixels into rank 0's raster image "
-                                         "over NVLink peer memory (CUDA IPC); barrier per step",
-                                  "nccl": "rgba8 all_gather_into_tensor per frame (async, double-"
-                                          "buffered) + untile on rank 0",
-                                  "none": "none"}[gather],
-                       "launch": "one persistent cooperative launch per frame; " + graph_note,
-                       "l2": "256 MiB memset between steps (outside the timed events); "
-                             "frames inside a step share L2 as in the real render loop"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "what": "upload_scene(host arrays) + F x render_frame + read_output_rgba8 "
-                            "into pinned memory, wall clock incl. synchronisation"},
+            "config": {"workload": describe(args, len(tris), len(nodes), W, H, F), "frames_per_step": F},
+            "run": {"samples_per_step": samples_per_step,
+                    "partition": f"16x16 tiles, tile_id % {world} == rank" if world > 1 else "none",
+                    "gather": {"p2p": "fused: the kernels store rgba8 pixels into rank 0's raster image over "
+                                      "NVLink peer memory (CUDA IPC); one barrier per step",
+                               "nccl": "one rgba8 all_gather_into_tensor per step + untile on rank 0",
+                               "none": "none"}[run.gather],
+                    "launch": ("one rvpt_b200_render_frame call per frame; " if args.frame_by_frame else
+                               f"one rvpt_b200_render_frames({F}) call per step = {st['kernel_launches']} batched "
+                               f"launch(es) of <= {n_f} frames; ") + launch_note,
+                    "l2": "256 MiB memset between steps (outside the timed events); inputs of a step "
+                          "(accumulation image, queues, parked samples: > 126 MB L2 per launch) stream from HBM"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
+                    "what": "upload_scene(host arrays) + render_frames + read_output_rgba8 into pinned "
+                            "memory, wall clock incl. synchronisation"},
             "gpu_launches": args.steps * launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "mrays_per_s": value * (R / max(S_local, 1)),
+            "parity_ok": parity_ok,
+            "parity": None if args.no_parity else {
+                "what": f"rgba8 image after the last timed step vs the CPU oracle's frames 0..{F - 1}",
+                "differing_pixels": getattr(run, "diff_pixels", None),
+                "image_sha256": getattr(run, "image_sha256", None)},
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "c4": c4,
+            "mrays_per_s": value * (R / max(S, 1)),
         }
         print(json.dumps(line))
     if world > 1:

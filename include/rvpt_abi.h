@@ -103,7 +103,7 @@ typedef struct rvpt_b200_stats
     uint64_t samples;                              /* pixels x aa x frames rendered by this ctx */
     uint64_t segments;                             /* intersect_scene calls = sum of active[] */
     uint64_t active[RVPT_MAX_BOUNCE_STATS];        /* rays traced at bounce b */
-    uint32_t kernel_launches;                      /* kernels launched for the frame */
+    uint32_t kernel_launches;                      /* kernels launched by the last render_frame(s) call */
     uint32_t traversal_order;                      /* 0 reference child order, 1 front to back (see REFERENCE_ORDER) */
     uint32_t frames;                               /* frames the counters cover (1 unless batched) */
     uint32_t reserved;

@@ -20,6 +20,30 @@ FLAG_BRUTE_FORCE = 0x4
 
 _lib = None
 
+# RVPT::RenderSettings, src/rvpt/rvpt.h:77-89 (the oracle's own copy: bench.py's reference arm
+# must not import the product package)
+RENDER_SETTINGS_DTYPE = np.dtype([
+    ("max_bounces", "<i4"), ("aa", "<i4"), ("current_frame", "<u4"), ("camera_mode", "<i4"),
+    ("top_left_render_mode", "<i4"), ("top_right_render_mode", "<i4"),
+    ("bottom_left_render_mode", "<i4"), ("bottom_right_render_mode", "<i4"), ("split_ratio", "<f4", 2)])
+assert RENDER_SETTINGS_DTYPE.itemsize == 40
+
+
+def settings(max_bounces: int = 8, aa: int = 1, frame: int = 0, camera_mode: int = 0, mode: int = 9) -> np.ndarray:
+    rs = np.zeros(1, RENDER_SETTINGS_DTYPE)
+    rs["max_bounces"], rs["aa"], rs["current_frame"], rs["camera_mode"] = max_bounces, aa, frame, camera_mode
+    for k in ("top_left", "top_right", "bottom_left", "bottom_right"):
+        rs[f"{k}_render_mode"] = mode
+    rs["split_ratio"] = (0.5, 0.5)
+    return rs
+
+
+def load_workload(name: str) -> dict:
+    """A committed bench workload (oracle/workloads/, written by tools/make_bench_workloads.py):
+    nodes, triangles (BVH order), materials, camera_16x9."""
+    with np.load(HERE / "workloads" / f"{name}.npz") as z:
+        return {k: z[k] for k in z.files}
+
 
 def build(force: bool = False) -> Path:
     src = HERE / "rvpt_oracle.cpp"

@@ -9,11 +9,11 @@ from .engine import Engine, EngineError, build_bvh, camera_data  # noqa: F401
 from .scene import (  # noqa: F401
     DIELECTRIC, LAMBERT, MIRROR, Scene, builtin_scene, cornell_scene, default_settings,
     displaced_sphere_scene, load_obj,
-    make_material, make_triangles,
+    make_material, make_triangles, tridel_scene,
 )
 
 __all__ = [
     "Engine", "EngineError", "build_bvh", "camera_data", "Scene", "builtin_scene", "cornell_scene",
-    "default_settings", "displaced_sphere_scene", "load_obj", "make_material", "make_triangles", "LAMBERT", "MIRROR",
+    "default_settings", "displaced_sphere_scene", "load_obj", "make_material", "make_triangles", "tridel_scene", "LAMBERT", "MIRROR",
     "DIELECTRIC",
 ]

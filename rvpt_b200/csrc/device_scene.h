@@ -13,7 +13,13 @@
 #define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
 #define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
-#define RVPT_QUEUE_OCTANTS 8u      /* sub-queues of a path queue: one per direction octant */
+/* Binned path queues (closed scenes): a queue is RVPT_SORT_BINS sub-queues — one per direction
+ * octant (3 bits) x origin cell (RVPT_SORT_CELL_BITS per axis of the scene's bounding box) —
+ * of bin_cap entries each, plus one overflow / unsorted sub-queue that can hold every path. The
+ * rays a warp of the next wave loads together (32 consecutive entries of one sub-queue) then walk
+ * the same octant's node array from nearby origins. */
+#define RVPT_SORT_CELL_BITS 1u
+#define RVPT_SORT_BINS (8u << (3u * RVPT_SORT_CELL_BITS))       /* 64 */
 /* batched launches (render_frames): a queued path carries `slot | frame_in_batch << 26` */
 #define RVPT_BATCH_SLOT_BITS 26u
 #define RVPT_BATCH_SLOT_MASK ((1u << RVPT_BATCH_SLOT_BITS) - 1u)
@@ -102,12 +108,14 @@ struct PathQueue
     float4* q3;
 };
 
-/* Per wave, in shared memory: how the wave's groups of L rays map to the eight sub-queues.
- * pre[o] = first group of octant o, pre[8] = number of groups, cnt[o] = rays in sub-queue o. */
+/* Per wave, in shared memory: how the wave's groups of L rays (32, or fewer when a small wave is
+ * spread over all warps) map to the sub-queues. pre[k] = first group of sub-queue k,
+ * pre[BINS + 1] = number of groups, cnt[k] = rays in sub-queue k (k = BINS: overflow / unsorted). */
 struct WaveGroups
 {
-    uint32_t pre[RVPT_QUEUE_OCTANTS + 1];
-    uint32_t cnt[RVPT_QUEUE_OCTANTS];
+    uint32_t pre[RVPT_SORT_BINS + 2];
+    uint32_t cnt[RVPT_SORT_BINS + 1];
+    uint32_t count; /* rays of the wave */
     uint32_t L;
 };
 
@@ -128,10 +136,9 @@ struct WaveCounters
     uint32_t work_ctr[64]; /* k_bounce (one launch per wave): the claimed eighth of wave b */
     /* k_frame's big bounce waves: sharded like chunk_ctr, wave b uses set b & 1 */
     uint32_t bounce_ctr[2][RVPT_CHUNK_SHARDS * 32u];
-    /* survivors pushed by bounce b (read by b+1), per direction octant of the pushed ray: every
-     * queue is eight sub-queues, so the rays a warp of the next wave loads together point into
-     * the same octant (they walk the same node array, in a similar order) */
-    uint32_t qcount[64][RVPT_QUEUE_OCTANTS];
+    /* survivors pushed by bounce b (read by b+1) per sub-queue; a binned sub-queue's counter may
+     * run past bin_cap (the excess went to the overflow sub-queue): readers clamp it */
+    uint32_t qcount[64][RVPT_SORT_BINS + 1];
 };
 struct FrameStats
 {
@@ -197,7 +204,12 @@ struct FrameParams
     float4* samples;
     uint32_t tail_threshold;      /* waves this small finish inside their threads */
     uint32_t use_forecast;        /* wave-size forecast from the previous launch is meaningful */
-    uint32_t queue_stride;        /* entries between the sub-queues of a PathQueue (0: one queue, no sorting) */
+    /* binned path queues (device_scene.h, RVPT_SORT_*): entries per binned sub-queue (0: the
+     * queues have only the unsorted sub-queue); the unsorted / overflow sub-queue starts at
+     * RVPT_SORT_BINS * bin_cap */
+    uint32_t bin_cap;
+    float sort_lo[3];             /* scene bounding box (root node) */
+    float sort_scale[3];          /* cells per unit: (1 << RVPT_SORT_CELL_BITS) / extent */
     unsigned long long* timeline; /* optional [n_ctas][RVPT_TIMELINE_SLOTS] globaltimer stamps */
 };
 

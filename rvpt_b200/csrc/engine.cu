@@ -47,8 +47,9 @@ struct rvpt_b200_ctx
     int l2_persist_max = 0; /* cudaDevAttrMaxPersistingL2CacheSize */
     int l2_window_max = 0;  /* cudaDevAttrMaxAccessPolicyWindowSize */
     int grid_frame = 0, grid_primary = 0, grid_bounce = 0;
-    uint32_t queue_stride = 0; /* entries per octant sub-queue; 0 = unsorted single queue */
-    bool queue_sorted = false; /* the queues are eight octant sub-queues */
+    uint32_t bin_cap = 0;            /* entries per binned sub-queue (0: unsorted sub-queue only) */
+    float sort_lo[3] = {0, 0, 0}, sort_scale[3] = {0, 0, 0}; /* scene box -> origin cells; scale 0: no sorting */
+    uint32_t batch_limit = 0;  /* set when an allocation failed: largest batch worth trying */
     uint32_t batch_cap = 0;    /* frames per launch the queues and the sample buffer hold (>= 1 once allocated) */
     size_t queue_budget = (size_t)64 << 30; /* bytes the path queues may take (of 180 GB) */
     uint32_t tail_rays_per_warp = 16; /* waves up to this many rays per resident warp finish in-thread (measured: 2..8 equal, 16 saves a barrier + wave on sparse poses) */
@@ -62,6 +63,8 @@ struct rvpt_b200_ctx
     unsigned char* h_scene_pinned = nullptr; /* staging copy of the blob */
     size_t scene_capacity = 0;
     cudaEvent_t scene_copied = nullptr;
+    size_t scene_blob_bytes = 0;             /* bytes of the packed blob in h_scene_pinned */
+    std::vector<unsigned char> scene_inputs; /* the caller's arrays of the last upload (exact compare) */
     SceneLayout layout{};
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
@@ -84,6 +87,7 @@ struct rvpt_b200_ctx
     int last_max_bounces = 0;
     int last_aa = 0;
     uint32_t last_launches = 0;
+    uint32_t call_launches = 0; /* launches of the render_frame(s) call in progress */
     uint32_t last_frames = 0; /* frames the last launch covered (stats) */
 
     /* per-CTA phase stamps of the last frame kernel (set_timeline) */
@@ -146,6 +150,7 @@ void free_queues(rvpt_b200_ctx* ctx)
     }
     cudaFree(ctx->d_samples);
     ctx->d_samples = nullptr;
+    ctx->bin_cap = 0;
     ctx->batch_cap = 0;
 }
 
@@ -167,24 +172,31 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
     ctx->buffers_ready = false;
 }
 
-/* Frames one launch may cover with the path queues inside their memory budget (every queue is
- * eight octant sub-queues, each able to hold every path of the launch: 8 x 64 B per pixel,
- * frame and queue — 2.1 GB per 1080p frame of a batch, 8.5 GB per 4K frame). */
+/* Frames one launch may cover with the path queues inside their memory budget. A queue holds
+ * 64 B per path; binned (closed-scene ray sorting, device_scene.h) it is RVPT_SORT_BINS
+ * sub-queues of an eighth of all paths each plus the overflow sub-queue that can hold them
+ * all: (BINS / 8 + 1) x 64 B per pixel and frame, two queues, + 16 B parked sample —
+ * 2.4 GB per 1080p frame of a batch, 9.7 GB per 4K frame (of 180 GB). */
+#define RVPT_BIN_SHARE 8u /* a binned sub-queue holds 1/8 of a launch's paths */
+size_t queue_bytes_per_entry(const rvpt_b200_ctx* ctx)
+{
+    const bool sorted = !(ctx->flags & (RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_UNFUSED));
+    return 2u * 64u * (sorted ? RVPT_SORT_BINS / RVPT_BIN_SHARE + 1u : 1u) + 16u;
+}
+
 uint32_t max_batch(const rvpt_b200_ctx* ctx)
 {
     const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
     if (slots == 0 || slots > RVPT_BATCH_SLOT_MASK) return 1;
-    const bool sorted = !(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT);
-    const size_t per_frame = slots * 64u * 2u * (sorted ? RVPT_QUEUE_OCTANTS : 1u);
-    size_t cap = ctx->queue_budget / per_frame;
+    size_t cap = ctx->queue_budget / (slots * queue_bytes_per_entry(ctx));
     cap = std::min<size_t>(cap, RVPT_MAX_BATCH);
-    cap = std::min<size_t>(cap, ((size_t)1 << 31) / slots); /* queue indices are 32-bit */
+    cap = std::min<size_t>(cap, ((size_t)1 << 28) / slots); /* queue indices are 32-bit, binned queues 9x */
+    if (ctx->batch_limit) cap = std::min<size_t>(cap, ctx->batch_limit); /* what the device could give */
     return (uint32_t)std::max<size_t>(cap, 1);
 }
 
 /* (Re)allocates the path queues and the parked-sample buffer for launches of up to `frames`
- * frames. Queues: eight sub-queues (one per direction octant of the queued ray) of
- * slots * batch_cap entries each while that fits the budget, else one unsorted queue. */
+ * frames. */
 int ensure_batch_capacity(rvpt_b200_ctx* ctx, uint32_t frames)
 {
     if (frames <= ctx->batch_cap) return 0;
@@ -192,20 +204,35 @@ int ensure_batch_capacity(rvpt_b200_ctx* ctx, uint32_t frames)
     CU(cudaStreamSynchronize(ctx->stream));
     free_queues(ctx);
     const size_t slots = (size_t)ctx->n_local_padded * RVPT_TILE_PIXELS;
-    const size_t per_queue = slots * frames; /* paths of one launch */
-    ctx->queue_sorted = !(ctx->flags & RVPT_B200_FLAG_NO_QUEUE_SORT) &&
-                        per_queue * 64u * 2u * RVPT_QUEUE_OCTANTS <= std::max(ctx->queue_budget, (size_t)16 << 30) &&
-                        per_queue * RVPT_QUEUE_OCTANTS < ((size_t)1 << 32);
-    ctx->queue_stride = ctx->queue_sorted ? (uint32_t)per_queue : 0u;
-    const size_t entries = std::max<size_t>(ctx->queue_sorted ? per_queue * RVPT_QUEUE_OCTANTS : per_queue, 1);
-    for (int i = 0; i < 2; ++i)
+    const size_t per_queue = std::max<size_t>(slots * frames, 1); /* paths of one launch */
+    /* binned while that stays below 16 GiB (single frames of huge images keep one sub-queue) */
+    bool sorted = !(ctx->flags & (RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_UNFUSED));
+    const size_t bin_cap = ((per_queue + RVPT_BIN_SHARE - 1) / RVPT_BIN_SHARE + 31) & ~(size_t)31;
+    size_t entries = per_queue + RVPT_SORT_BINS * bin_cap;
+    if (sorted && (entries * 128u > std::max(ctx->queue_budget, (size_t)16 << 30) || entries >= ((size_t)1 << 32)))
+        sorted = false;
+    if (!sorted) entries = per_queue;
+    ctx->bin_cap = sorted ? (uint32_t)bin_cap : 0u;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i)
     {
-        CU(cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4)));
-        CU(cudaMalloc(&ctx->queue[i].q3, entries * sizeof(float4)));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->queue[i].q0, entries * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->queue[i].q1, entries * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->queue[i].q2, entries * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->queue[i].q3, entries * sizeof(float4));
     }
-    if (frames > 1) CU(cudaMalloc(&ctx->d_samples, std::max<size_t>(per_queue, 1) * sizeof(float4)));
+    if (e == cudaSuccess && frames > 1) e = cudaMalloc(&ctx->d_samples, per_queue * sizeof(float4));
+    if (e == cudaErrorMemoryAllocation && frames > 1)
+    {
+        /* the device cannot give that much right now: halve the batch (render_frames re-plans) */
+        cudaGetLastError();
+        free_queues(ctx);
+        ctx->batch_limit = frames / 2u;
+        return ensure_batch_capacity(ctx, frames / 2u) ? RVPT_B200_ENOMEM : RVPT_B200_ENOMEM;
+    }
+    if (e != cudaSuccess)
+        return fail(ctx, e == cudaErrorMemoryAllocation ? RVPT_B200_ENOMEM : RVPT_B200_ECUDA,
+                    "path queue allocation failed: %s", cudaGetErrorString(e));
     ctx->batch_cap = frames;
     return 0;
 }
@@ -668,10 +695,24 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     else
         CU(cudaEventSynchronize(ctx->scene_copied)); /* the previous upload has left the staging copy */
     std::memcpy(ctx->h_scene_pinned, blob.data(), blob_bytes);
+    ctx->scene_blob_bytes = blob_bytes;
     CU(cudaMemcpyAsync(ctx->d_scene, ctx->h_scene_pinned, blob_bytes, cudaMemcpyHostToDevice,
                        ctx->stream));
     CU(cudaEventRecord(ctx->scene_copied, ctx->stream));
 
+    {
+        /* scene bounding box (root node) -> origin cells of the binned ray sort */
+        const DevNode& r = ps.nodes[0];
+        const float lo[3] = {r.bmin_x, r.bmin_y, r.bmin_z}, hi[3] = {r.bmax_x, r.bmax_y, r.bmax_z};
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) ok = ok && std::isfinite(lo[a]) && std::isfinite(hi[a]) && hi[a] >= lo[a];
+        for (int a = 0; a < 3; ++a)
+        {
+            ctx->sort_lo[a] = ok ? lo[a] : 0.0f;
+            const float ext = ok ? std::max(hi[a] - lo[a], 1e-20f) : 1.0f;
+            ctx->sort_scale[a] = ok ? (float)(1u << RVPT_SORT_CELL_BITS) / ext : 0.0f;
+        }
+    }
     const bool same_shape = ctx->have_scene && L.bytes == ctx->layout.bytes &&
                             L.n_nodes == ctx->layout.n_nodes && L.n_tris == ctx->layout.n_tris &&
                             oct == ctx->scene_oct;
@@ -834,6 +875,36 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
     if (n_triangles > 0x7FFFFFFFu) return fail(ctx, RVPT_B200_EUNSUPPORTED, "too many triangles");
 
     const bool brute = (ctx->flags & RVPT_B200_FLAG_BRUTE_FORCE) != 0;
+    /* The reference copies its scene buffers every frame (rvpt.cpp:123-126) although they never
+     * change after initialize(): when the caller's arrays equal the previous upload byte for
+     * byte, the packed blob still sitting in the pinned staging buffer is copied again (the
+     * host -> device transfer stays) and the packing work — BVH re-layout, per-triangle
+     * precomputation, coincident-face check, octant layouts — is skipped. */
+    {
+        const size_t nb = nodes ? n_nodes * sizeof(rvpt_bvh_node) : 0;
+        const size_t tb = n_triangles * sizeof(rvpt_triangle), mb = n_materials * sizeof(rvpt_material);
+        const size_t hdr = 3 * sizeof(size_t);
+        const size_t counts[3] = {nodes ? n_nodes : (size_t)-1, n_triangles, n_materials};
+        bool same = ctx->have_scene && ctx->scene_blob_bytes != 0 && ctx->scene_inputs.size() == hdr + nb + tb + mb &&
+                    std::memcmp(ctx->scene_inputs.data(), counts, hdr) == 0 &&
+                    (nb == 0 || std::memcmp(ctx->scene_inputs.data() + hdr, nodes, nb) == 0) &&
+                    std::memcmp(ctx->scene_inputs.data() + hdr + nb, triangles, tb) == 0 &&
+                    std::memcmp(ctx->scene_inputs.data() + hdr + nb + tb, materials, mb) == 0;
+        if (same)
+        {
+            CU(cudaSetDevice(ctx->device));
+            CU(cudaMemcpyAsync(ctx->d_scene, ctx->h_scene_pinned, ctx->scene_blob_bytes, cudaMemcpyHostToDevice,
+                               ctx->stream));
+            CU(cudaEventRecord(ctx->scene_copied, ctx->stream));
+            return 0;
+        }
+        ctx->scene_blob_bytes = 0; /* invalid until this upload succeeds */
+        ctx->scene_inputs.resize(hdr + nb + tb + mb);
+        std::memcpy(ctx->scene_inputs.data(), counts, hdr);
+        if (nb) std::memcpy(ctx->scene_inputs.data() + hdr, nodes, nb);
+        std::memcpy(ctx->scene_inputs.data() + hdr + nb, triangles, tb);
+        std::memcpy(ctx->scene_inputs.data() + hdr + nb + tb, materials, mb);
+    }
     PackedScene ps;
     int rc;
     if (!nodes && !brute)
@@ -922,7 +993,10 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
     p.timeline = ctx->d_timeline;
-    p.queue_stride = ctx->queue_stride;
+    /* binned queues (closed scenes): the origin cells need a finite scene box; without one
+     * every ray of an octant lands in that octant's cell 0 */
+    p.bin_cap = ctx->bin_cap;
+    for (int a = 0; a < 3; ++a) p.sort_lo[a] = ctx->sort_lo[a], p.sort_scale[a] = ctx->sort_scale[a];
     p.n_batch = n_batch;
     p.samples = ctx->d_samples;
     p.sample_stride = ctx->n_local_padded * RVPT_TILE_PIXELS;
@@ -977,7 +1051,8 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     ctx->frame_rendered = true;
     ctx->last_max_bounces = rs->max_bounces;
     ctx->last_aa = rs->aa;
-    ctx->last_launches = launches;
+    ctx->last_launches = ctx->call_launches + launches; /* of the whole render_frame(s) call so far */
+    ctx->call_launches = ctx->last_launches;
     ctx->last_frames = std::max(n_batch, 1u);
     return 0;
 }
@@ -1010,6 +1085,7 @@ extern "C" int rvpt_b200_render_frame(rvpt_b200_ctx* ctx, const rvpt_render_sett
     if (!ctx) return RVPT_B200_EINVAL;
     const int rc = validate_frame(ctx, rs, camera);
     if (rc) return rc;
+    ctx->call_launches = 0;
     return render_launches(ctx, rs, camera, 0);
 }
 
@@ -1020,6 +1096,7 @@ extern "C" int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_set
     int rc = validate_frame(ctx, rs, camera);
     if (rc) return rc;
     rvpt_render_settings s = *rs;
+    ctx->call_launches = 0;
     const bool kajiya = s.top_left_render_mode == 9 && s.top_right_render_mode == 9 &&
                         s.bottom_left_render_mode == 9 && s.bottom_right_render_mode == 9;
     /* Batched launches: the frames' waves are merged (kernels.cu, k_frame<.., kBatch>). Needs
@@ -1038,12 +1115,18 @@ extern "C" int rvpt_b200_render_frames(rvpt_b200_ctx* ctx, const rvpt_render_set
         return 0;
     }
     /* as few launches as the queue budget allows, of equal size */
-    const uint32_t n_launches = (n_frames + cap - 1) / cap;
-    const uint32_t per = (n_frames + n_launches - 1) / n_launches;
+    uint32_t n_launches = (n_frames + cap - 1) / cap;
+    uint32_t per = (n_frames + n_launches - 1) / n_launches;
     for (uint32_t done = 0; done < n_frames;)
     {
         const uint32_t n = std::min(per, n_frames - done);
-        if ((rc = render_launches(ctx, &s, camera, n))) return rc;
+        rc = render_launches(ctx, &s, camera, n);
+        if (rc == RVPT_B200_ENOMEM && ctx->batch_limit && ctx->batch_limit < per)
+        {
+            per = ctx->batch_limit; /* the queues did not fit the device: smaller batches */
+            continue;
+        }
+        if (rc) return rc;
         s.current_frame += n;
         done += n;
     }

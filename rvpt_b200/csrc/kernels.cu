@@ -234,10 +234,32 @@ __device__ __forceinline__ SceneViewT<kSmem> make_view(const unsigned char* base
 
 /* ---- nearest hit: stackless walk in the reference's visiting order ------- */
 
+/* Walks that do not visit the BVH in the reference's order (front to back) can only disagree
+ * with the reference's result (strict `t < closest_t`: the first triangle visited keeps a tie;
+ * a leaf box whose slab entry rounds above closest_t is culled even if its triangle's plane t
+ * rounds below it) when a SECOND accepted triangle lies within rounding distance of the nearest
+ * one: a shared edge, a corner, crossing surfaces. Such walks therefore run RELAXED, at no extra
+ * instruction in the node or plane tests: the loop carries clip_t = closest_t * (1 + 3 * 2^-12)
+ * instead of closest_t — boxes and plane tests are clipped against it, so every triangle within
+ * the band of the nearest one is seen — and an accepted triangle that finds or leaves another one
+ * inside the band flags the hit AMBIGUOUS (top bit of the triangle index). trace_nearest()
+ * re-traces flagged rays (about one in a million) with the reference's own walk, and recomputes
+ * the exact t of the others from the winning triangle (same operations, same bits). The band is
+ * far above the rounding error of t (a few ulp; more at grazing incidence) and far below any
+ * geometric separation. Found by the full-size parity runs of round 2: without it, 2 of 1.3e8
+ * samples of the pinned pose and 1 of 3.3e7 of the Cornell box picked another triangle. */
+#define RVPT_TIE_BAND 1.000732421875f  /* 1 + 3 * 2^-12 */
+#define RVPT_TRI_AMBIGUOUS 0x80000000u
+
+__device__ __forceinline__ bool hit_is_ambiguous(uint32_t best_tri)
+{
+    return (best_tri ^ RVPT_TRI_AMBIGUOUS) < 0x7FFFFFFFu; /* flag set on a valid index (not 0xFFFFFFFF) */
+}
+
 /* Leaf: intersect_triangle_fast (intersection.glsl:267-323) on the precomputed
  * records of one leaf; the early-out after the plane test is value-neutral
- * because the acceptance test is a pure conjunction. */
-template <bool kSmem, bool kRel>
+ * because the acceptance test is a pure conjunction. kRelaxed: best_t is clip_t (see above). */
+template <bool kSmem, bool kRel, bool kRelaxed>
 __device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d, uint32_t i,
                                           float& best_t, uint32_t& best_tri)
 {
@@ -266,8 +288,23 @@ __device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, 
             const float v = A.w * (m2 + m3);
             if (0.0f < u && 0.0f < v && u + v < 1.0f)
             {
-                best_t = t;
-                best_tri = i;
+                if constexpr (kRelaxed)
+                {
+                    const float tc = t * RVPT_TIE_BAND;
+                    if (tc < best_t)
+                    {
+                        /* new nearest; the previous one may still lie inside its band */
+                        best_tri = (best_t <= tc * RVPT_TIE_BAND) ? (i | RVPT_TRI_AMBIGUOUS) : i;
+                        best_t = tc;
+                    }
+                    else
+                        best_tri |= RVPT_TRI_AMBIGUOUS; /* inside the band of the nearest (or an exact tie) */
+                }
+                else
+                {
+                    best_t = t;
+                    best_tri = i;
+                }
             }
         }
         ++i;
@@ -285,6 +322,9 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
                                              rv_f3 d, float ix, float iy, float iz, float& best_t,
                                              uint32_t& best_tri)
 {
+    /* the octant arrays may be in front-to-back order: relaxed walk, best_t is the clip
+     * distance closest_t * RVPT_TIE_BAND until trace_nearest() recomputes the exact t */
+    constexpr bool kRelaxed = kSorted;
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
@@ -332,7 +372,7 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
         {
             if (leaf != RVPT_NODE_INNER)
             {
-                test_leaf<kSmem, kRel>(sc, o, d, leaf, best_t, best_tri);
+                test_leaf<kSmem, kRel, kRelaxed>(sc, o, d, leaf, best_t, best_tri);
                 node = skip;
             }
             else
@@ -341,6 +381,24 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
         else
             node = skip;
     }
+}
+
+/* The reference's walk for the rare ray whose front-to-back result is ambiguous. Out of line
+ * on purpose: one copy per kernel, and its registers are not the hot loops' problem. Shared-
+ * memory scenes only (the global path always walks the reference's order). */
+__device__ __noinline__ void retrace_reference_order(uint32_t nodes, uint32_t tris, uint32_t meta, rv_f3 o,
+                                                     rv_f3 d, float* best_t, uint32_t* best_tri)
+{
+    SceneViewT<true> sc;
+    sc.nodes = nodes, sc.tris = tris, sc.meta = meta, sc.mats = 0;
+    sc.rel_nodes = sc.rel_num = sc.oct_nodes = sc.oct_rel_nodes = 0;
+    sc.oct_stride = 0;
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    float t = RV_INF;
+    uint32_t tri = 0xFFFFFFFFu;
+    walk_nearest<true, false, false>(sc, sc.nodes, o, d, ix, iy, iz, t, tri);
+    *best_t = t;
+    *best_tri = tri;
 }
 
 template <bool kSmem, bool kRel, bool kOct>
@@ -368,6 +426,25 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
              * constant-bank loads, octant bits) inside the node loop to save a register */
             asm volatile("" : "+r"(base));
             walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+            if (best_tri != 0xFFFFFFFFu)
+            {
+#ifndef RVPT_PROBE_NO_RETRACE
+                if (hit_is_ambiguous(best_tri))
+                    /* a runner-up within rounding distance of the nearest hit: the reference's own
+                     * walk decides (plain node array, reference child order, exact clipping) */
+                    retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d, &best_t, &best_tri);
+                else
+#endif
+                {
+                    /* the relaxed walk carried the clip distance: the hit's t, recomputed with the
+                     * operations of the plane test (same inputs, same bits) */
+                    const float4 A = ld_f4<kSmem>(sc.tris, 4 * best_tri + 0);
+                    const float4 B = ld_f4<kSmem>(sc.tris, 4 * best_tri + 1);
+                    const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, best_tri))
+                                           : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
+                    best_t = num / rv_dot(d, rv_make(B.x, B.y, B.z));
+                }
+            }
         }
         else
             walk_nearest<kSmem, false, false>(sc, sc.nodes, o, d, ix, iy, iz, best_t, best_tri);
@@ -626,36 +703,54 @@ __device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathSta
     return false;
 }
 
-/* Warp-aggregated append of the surviving lanes to a queue: the lanes are grouped by the
- * direction octant of their new ray (match.any), each group appends to that octant's
- * sub-queue with one atomicAdd. qcount8 = the eight counters of this wave. */
+/* Warp-aggregated append of the surviving lanes to a queue. Unsorted (open scenes: rays of
+ * neighbouring pixels, whatever their direction, walk more alike than same-bin rays from all
+ * over the image): ballot + one atomicAdd per warp into the unsorted sub-queue, 4 x 512
+ * contiguous bytes per full warp. Sorted (closed scenes): the lanes are grouped by the bin of
+ * their new ray — direction octant x origin cell — with match.any, each group appends to that
+ * bin's sub-queue with one atomicAdd; what does not fit a bin goes to the overflow sub-queue.
+ * Which warp traces a path never changes the path: sorting is scheduling only.
+ * qcount = the RVPT_SORT_BINS + 1 counters of this wave. All 32 lanes must call. */
 __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQueue& q,
-                                               uint32_t* qcount8, bool alive, uint32_t slot,
+                                               uint32_t* qcount, bool alive, uint32_t slot,
                                                const PathState& s, bool sort)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
     if (mask == 0) return;
+    const uint32_t ovf_base = RVPT_SORT_BINS * p.bin_cap;
     uint32_t i = 0;
-    if (!sort)
+    bool spill = alive; /* lanes that go to the unsorted / overflow sub-queue */
+    if (sort)
     {
-        /* unsorted frames (open scenes: rays from neighbouring pixels, whatever their direction,
-         * walk more alike than same-octant rays from all over the image) use sub-queue 0 only */
-        uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(&qcount8[0], (uint32_t)__popc(mask));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
-        i = base + __popc(mask & ((1u << lane) - 1u));
+        if (alive)
+        {
+            constexpr uint32_t kMax = (1u << RVPT_SORT_CELL_BITS) - 1u;
+            /* statistics, not rendering arithmetic: any cell assignment gives the same image */
+            const uint32_t cx = min((uint32_t)fmaxf((s.o.x - p.sort_lo[0]) * p.sort_scale[0], 0.0f), kMax);
+            const uint32_t cy = min((uint32_t)fmaxf((s.o.y - p.sort_lo[1]) * p.sort_scale[1], 0.0f), kMax);
+            const uint32_t cz = min((uint32_t)fmaxf((s.o.z - p.sort_lo[2]) * p.sort_scale[2], 0.0f), kMax);
+            const uint32_t oct = (__float_as_uint(s.d.x) >> 31) | ((__float_as_uint(s.d.y) >> 31) << 1) |
+                                 ((__float_as_uint(s.d.z) >> 31) << 2);
+            const uint32_t bin = (((oct << RVPT_SORT_CELL_BITS | cz) << RVPT_SORT_CELL_BITS | cy) << RVPT_SORT_CELL_BITS) | cx;
+            const uint32_t peers = __match_any_sync(mask, bin);
+            const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&qcount[bin], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t my = base + __popc(peers & ((1u << lane) - 1u));
+            spill = my >= p.bin_cap;
+            i = bin * p.bin_cap + my;
+        }
     }
-    else if (alive)
+    const uint32_t smask = __ballot_sync(0xFFFFFFFFu, spill);
+    if (smask)
     {
-        const uint32_t oct = (__float_as_uint(s.d.x) >> 31) | ((__float_as_uint(s.d.y) >> 31) << 1) |
-                             ((__float_as_uint(s.d.z) >> 31) << 2);
-        const uint32_t peers = __match_any_sync(mask, oct);
-        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
         uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&qcount8[oct], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        i = oct * p.queue_stride + base + __popc(peers & ((1u << lane) - 1u));
+        const uint32_t first = (uint32_t)(__ffs(smask) - 1);
+        if (lane == first) base = atomicAdd(&qcount[RVPT_SORT_BINS], (uint32_t)__popc(smask));
+        base = __shfl_sync(0xFFFFFFFFu, base, first);
+        if (spill) i = ovf_base + base + __popc(smask & ((1u << lane) - 1u));
     }
     if (alive)
     {
@@ -668,49 +763,40 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
     }
 }
 
-/* A wave's eight sub-queue counters: every warp loads them (lane o holds counter o) and gets
- * their total (warp-uniform); *mine = this lane's counter. */
-__device__ __forceinline__ uint32_t wave_count(const uint32_t* qcount8, uint32_t* mine)
+/* Deal a wave: reads its sub-queue counters, L rays per group (32, or fewer when the wave is
+ * spread over all warps), groups numbered sub-queue by sub-queue. Block-wide (ends with a
+ * barrier); wg lives in shared memory and its previous readers are behind the grid barrier /
+ * kernel boundary that precedes every wave. Returns the wave's ray count (block-uniform). */
+__device__ __forceinline__ uint32_t prepare_wave(const FrameParams& p, WaveGroups& wg, const uint32_t* qcount,
+                                                 uint32_t spread_below)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t c = lane < RVPT_QUEUE_OCTANTS ? *reinterpret_cast<const volatile uint32_t*>(&qcount8[lane]) : 0u;
-    *mine = c;
-    uint32_t t = c;
-#pragma unroll
-    for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
-    return __shfl_sync(0xFFFFFFFFu, t, 0);
-}
-
-/* Deal a wave: L rays per group (32, or fewer when the wave is spread over all warps), groups
- * numbered octant by octant. Warp 0 writes the table from the counters it already holds
- * (wave_count); block-wide (ends with a barrier); wg lives in shared memory and its previous
- * readers are behind the grid barrier / kernel boundary that precedes every wave. */
-__device__ __forceinline__ void prepare_wave(WaveGroups& wg, uint32_t mine, uint32_t count, bool spread)
-{
-    if (threadIdx.x < 32u)
+    constexpr uint32_t kQ = RVPT_SORT_BINS + 1u;
+    for (uint32_t k = threadIdx.x; k < kQ; k += blockDim.x)
     {
-        const uint32_t lane = threadIdx.x;
-        const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-        /* spread: every warp gets one group even though each octant rounds its last group up */
-        const uint32_t share = n_warps > 2u * RVPT_QUEUE_OCTANTS ? n_warps - RVPT_QUEUE_OCTANTS : n_warps;
-        const uint32_t L = spread ? max(1u, min(32u, (count + share - 1u) / share)) : 32u;
-        const uint32_t g = (mine + L - 1u) / L;
-        uint32_t incl = g; /* inclusive scan over the eight octants */
-#pragma unroll
-        for (int d = 1; d < (int)RVPT_QUEUE_OCTANTS; d <<= 1)
-        {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        if (lane < RVPT_QUEUE_OCTANTS)
-        {
-            wg.cnt[lane] = mine;
-            wg.pre[lane] = incl - g;
-        }
-        if (lane == RVPT_QUEUE_OCTANTS - 1u) wg.pre[RVPT_QUEUE_OCTANTS] = incl;
-        if (lane == 0) wg.L = L;
+        const uint32_t c = *reinterpret_cast<const volatile uint32_t*>(&qcount[k]);
+        wg.cnt[k] = k < RVPT_SORT_BINS ? min(c, p.bin_cap) : c;
     }
     __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t count = 0;
+        for (uint32_t k = 0; k < kQ; ++k) count += wg.cnt[k];
+        const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+        /* spread: every warp gets one group even though each sub-queue rounds its last group up */
+        const uint32_t share = n_warps > 2u * kQ ? n_warps - kQ : n_warps;
+        const uint32_t L = count <= spread_below ? max(1u, min(32u, (count + share - 1u) / share)) : 32u;
+        uint32_t g = 0;
+        for (uint32_t k = 0; k < kQ; ++k)
+        {
+            wg.pre[k] = g;
+            g += (wg.cnt[k] + L - 1u) / L;
+        }
+        wg.pre[kQ] = g;
+        wg.count = count;
+        wg.L = L;
+    }
+    __syncthreads();
+    return wg.count;
 }
 
 /* mat4 * vec4(x,y,z,w).xyz with the columns summed left to right. */
@@ -1006,7 +1092,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     /* spread: L lanes per warp and round; otherwise full 32-ray groups (prepare_wave) */
     const uint32_t L = wg.L;
-    const uint32_t groups = wg.pre[RVPT_QUEUE_OCTANTS];
+    const uint32_t groups = wg.pre[RVPT_SORT_BINS + 1u];
     const uint32_t per_warp = groups / n_warps;
     const uint32_t static_rounds = spread ? (groups + n_warps - 1) / n_warps : per_warp - (per_warp >> 3);
     const uint32_t dyn_base = static_rounds * n_warps;
@@ -1043,17 +1129,19 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
         if (!sharded && !spread && round + 1 >= static_rounds && lane == 0)
             claim = atomicAdd(&wc.work_ctr[b], 1u);
 
-        /* group g -> (octant, group inside its sub-queue): the last octant whose first group is <= g */
-        uint32_t o = g >= wg.pre[4] ? 4u : 0u;
-        o += g >= wg.pre[o + 2u] ? 2u : 0u;
-        o += g >= wg.pre[o + 1u] ? 1u : 0u;
-        const uint32_t i = (g - wg.pre[o]) * L + lane;
+        /* group g -> (sub-queue, group inside it): the last sub-queue whose first group is <= g
+         * (binary search over the prefix table in shared memory) */
+        uint32_t k = 0;
+#pragma unroll
+        for (uint32_t step = RVPT_SORT_BINS; step > 0; step >>= 1)
+            if (k + step <= RVPT_SORT_BINS && wg.pre[k + step] <= g) k += step;
+        const uint32_t i = (g - wg.pre[k]) * L + lane;
         bool alive = false;
         PathState s;
         uint32_t slot = 0;
-        if (lane < L && i < wg.cnt[o])
+        if (lane < L && i < wg.cnt[k])
         {
-            load_path(qin, o * p.queue_stride + i, s, slot); /* slot: the path's tag */
+            load_path(qin, k * p.bin_cap + i, s, slot); /* slot: the path's tag */
             if constexpr (!kBatch) prefetch_prev(p, slot);
             rv_f3 sample;
             for (int k = b;; ++k)
@@ -1313,9 +1401,10 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     if constexpr (!kSmem) __syncthreads(); /* the global path stages nothing: publish the forecast */
     stamp(p, 1);
 
-    /* closed scenes (most bounce rays hit something) queue their survivors by direction octant;
-     * ordered_bounce is visible to everybody since the barriers of setup_scene */
-    const bool sort = p.queue_stride != 0u && ordered_bounce != 0u;
+    /* closed scenes (most bounce rays hit something) queue their survivors by bin — direction
+     * octant x origin cell; ordered_bounce is visible to everybody since the barriers of
+     * setup_scene */
+    const bool sort = p.bin_cap != 0u && ordered_bounce != 0u;
     primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
     stamp(p, 2);
 
@@ -1323,10 +1412,10 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
     bool synced = false; /* a grid barrier has been passed since the last sample was parked */
     for (int b = 1; b < p.max_bounces; ++b)
     {
-        grid.sync(); /* wave b-1 is complete: its survivor count is final */
+        grid.sync(); /* wave b-1 is complete: its survivor counts are final */
         stamp(p, 2 * b + 1);
-        uint32_t my_count;
-        const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
+        const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+        const uint32_t count = prepare_wave(p, wg, wc.qcount[b - 1], 64u * n_warps);
         if (count == 0)
         {
             synced = true;
@@ -1334,8 +1423,6 @@ __global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FramePa
         }
         if (blockIdx.x == 0 && threadIdx.x == 0 && b < RVPT_MAX_BOUNCE_STATS)
             atomicAdd(&p.ctr->stats.active[b], (unsigned long long)count);
-        const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-        prepare_wave(wg, my_count, count, count <= 64u * n_warps);
         if (count <= p.tail_threshold)
         {
             bounce_phase<kSmem, kOct, true, kBatch>(p, sc, b, wg, RVPT_WAVE_SPREAD, sort);
@@ -1384,7 +1471,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const FrameParams p)
     }
     else
         sc = make_view<false>(p.scene, p.layout);
-    primary_phase<kSmem, false, false>(p, sc, p.queue_stride != 0u);
+    primary_phase<kSmem, false, false>(p, sc, false); /* one launch per wave: push order, no sort */
     finish_launch(p);
 }
 
@@ -1396,8 +1483,8 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
 
     WaveCounters& wc = p.ctr->wave;
     __shared__ WaveGroups wg;
-    uint32_t my_count;
-    const uint32_t count = wave_count(wc.qcount[b - 1], &my_count);
+    const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+    const uint32_t count = prepare_wave(p, wg, wc.qcount[b - 1], 64u * n_warps);
     if (count == 0) /* an empty wave costs nothing but the launch */
     {
         finish_launch(p);
@@ -1414,10 +1501,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const FrameParams p, const 
     }
     else
         sc = make_view<false>(p.scene, p.layout);
-    const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-    prepare_wave(wg, my_count, count, count <= 64u * n_warps);
-    bounce_phase<kSmem, false, false>(p, sc, b, wg, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u,
-                                      p.queue_stride != 0u);
+    bounce_phase<kSmem, false, false>(p, sc, b, wg, count <= 64u * n_warps ? RVPT_WAVE_SPREAD : 0u, false);
     finish_launch(p);
 }
 

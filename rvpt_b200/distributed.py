@@ -39,11 +39,23 @@ class FrameGather:
         self.side = torch.cuda.Stream(device=device)
         self.pending = [None, None]   # (work, untile-done event) of the last gather per buffer
         self.parity = 0
+        # every wait below is enqueued on torch's current stream, so the engine must launch its
+        # kernels there too — on its own stream the collective could read a slot the frame kernel
+        # is still writing, and the next frame could overwrite a slot a gather is still reading
+        self.stream = torch.cuda.current_stream(device)
+        engine.set_stream(self.stream.cuda_stream)
         engine.set_external_tiles(None, self.my_slot[0].data_ptr())
+
+    def _check_stream(self) -> None:
+        cur = self.torch.cuda.current_stream()
+        if cur.cuda_stream != self.stream.cuda_stream:
+            raise RuntimeError("FrameGather is bound to the stream that was current when it was created; "
+                               "call it under that stream (torch.cuda.stream(...))")
 
     def begin_frame(self) -> None:
         """Call before render_frame: points the kernels at the buffer of this
         frame and makes the render stream wait for its previous gather."""
+        self._check_stream()
         b = self.parity
         pend = self.pending[b]
         if pend is not None:
@@ -57,6 +69,7 @@ class FrameGather:
     def end_frame(self) -> None:
         """Call after render_frame: ONE collective for the frame, asynchronous;
         the scatter into the raster image follows it on the side stream."""
+        self._check_stream()
         b = self.parity
         work = self.dist.all_gather_into_tensor(self.gathered[b], self.my_slot[b], async_op=True)
         done = None

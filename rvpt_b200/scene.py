@@ -246,6 +246,28 @@ def displaced_sphere_scene(n_triangles: int = 20000, seed: int = 1) -> Scene:
     return Scene(np.concatenate([tris, ground]), mats, f"displaced_sphere_{len(tris) + 2}")
 
 
+TRIDEL_NPZ = ASSETS / "tridel_interior.npz"
+
+
+def tridel_scene() -> tuple[Scene, tuple[float, float, float], float]:
+    """The reference's large test model, assets/models/tridel-interior-test.obj (560 021
+    triangles), from the packed copy tools/pack_tridel.py writes next to the
+    reference tree (rvpt_b200/assets/tridel_interior.npz: git-ignored, travels with the repo
+    snapshot). One white Lambert material like `load_model(rvpt, path, material_id)`
+    (main.cpp:12-62) plus the unused emissive material 0 of main.cpp:102-107; the degenerate
+    triangles of the file (1 318 with zero area) are kept — the reference uploads them too.
+    Returns (scene, camera pose inside the room, fov)."""
+    if not TRIDEL_NPZ.exists():
+        raise FileNotFoundError(f"{TRIDEL_NPZ} is missing: run tools/pack_tridel.py next to the reference tree")
+    data = np.load(TRIDEL_NPZ)
+    tris = triangles_from_mesh(data["vertices"], data["faces"], 1)
+    mats = np.concatenate([
+        make_material((1, 1, 1, 0), (0.1, 0.4, 0.6, 0), LAMBERT),
+        make_material((0.8, 0.8, 0.8, 0), (0, 0, 0, 0), LAMBERT),
+    ])
+    return Scene(tris, mats, "tridel_interior"), (-2.5, 1.5, -1.0), 75.0
+
+
 def default_settings(max_bounces: int = 8, aa: int = 1, frame: int = 0, camera_mode: int = 0,
                      mode: int = 9) -> np.ndarray:
     """`RVPT::RenderSettings` defaults (src/rvpt/rvpt.h:77-89); the first

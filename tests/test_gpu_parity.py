@@ -628,10 +628,11 @@ def test_front_to_back_order_equals_reference_order(rv, oracle_mod, builtin, cor
 
 @pytest.mark.parametrize("unfused", [False, True])
 def test_octant_sorted_queues_are_scheduling_only(rv, oracle_mod, cornell, unfused):
-    """Survivors are queued in eight sub-queues by the direction octant of their new ray, so the
-    rays a warp loads together walk the same node array. Which warp traces a path never changes the
-    path: images and per-bounce counts equal the oracle's with and without the sorting, fused and
-    one-launch-per-wave, incl. a spread tail (small image) and aa passes."""
+    """In closed scenes every wave's rays are sorted into bins (direction octant x origin cell),
+    so the rays a warp loads together walk the same node array along similar paths. Which warp
+    traces a path never changes the path: images and per-bounce counts equal the oracle's with
+    and without the sorting (one-launch-per-wave never sorts), incl. a spread tail (small image)
+    and aa passes."""
     from rvpt_b200 import _lib
     base = _lib.FLAG_UNFUSED if unfused else 0
     for W, H, kw in ((200, 152, dict(frames=3)), (48, 40, dict(frames=2, aa=2)), (640, 360, dict(frames=2))):
@@ -735,9 +736,10 @@ def test_batched_launch_partition_and_large_scene(rv, oracle_mod, builtin):
 
 
 def test_batch_size_follows_the_queue_budget(rv, oracle_mod, builtin, monkeypatch):
-    """The path queues of a launch must fit RVPT_B200_QUEUE_BUDGET_MIB: 256x256 needs 64 MiB per
-    frame of a batch (8 octant sub-queues x 2 queues x 64 B), so 200 MiB allows 3 frames."""
-    monkeypatch.setenv("RVPT_B200_QUEUE_BUDGET_MIB", "200")
+    """The path queues of a launch must fit RVPT_B200_QUEUE_BUDGET_MIB: 256x256 needs 9.75 MiB per
+    frame of a batch (2 queues x 64 B + 12 B sort key / permutation + 16 B parked sample per
+    pixel), so 35 MiB allows 3 frames."""
+    monkeypatch.setenv("RVPT_B200_QUEUE_BUDGET_MIB", "35")
     eng, ora = _batched_vs_oracle(rv, oracle_mod, builtin, 256, 256, DEFAULT_POSE, [7])
     assert eng.stats()["frames"] == 1  # 7 frames -> launches of 3, 3, 1
     _assert_bit_equal(eng.read_accum_f32(), ora.accum, "budget-limited batches")
@@ -773,3 +775,56 @@ def test_cuda_graph_replay_is_safe_for_any_launch_count(rv, oracle_mod, builtin,
         _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"graph replay {replay}")
     eng.set_stream(None)
     eng.close()
+
+
+@pytest.mark.parametrize("case", ["pinned", "cornell"])
+def test_full_size_repeated_launches_stay_exact(rv, oracle_mod, builtin, cornell, case):
+    """Full-size batches launched repeatedly on one engine, so that every scheduling mode the
+    previous launch's statistics switch on is in effect (wave forecast, front-to-back bounce
+    arrays, binned ray sort): every pixel equals the oracle after each repetition. At this scale
+    (1e8 rays) some rays do hit a shared edge or a corner within rounding distance — where the
+    front-to-back walk alone would pick another triangle than the reference's walk (round 2 found
+    2 such pixels in the pinned pose, 1 in the Cornell box); the ambiguity re-trace must catch them."""
+    W, H = 1920, 1080
+    prep, pose, fov, n = (builtin, PINNED_POSE, 90.0, 64) if case == "pinned" else (cornell, CORNELL_POSE, 60.0, 16)
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    for f in range(n):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    for rep in range(3):
+        eng.render_frames(rv.default_settings(frame=0), cam, n)
+        _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"{case}, repetition {rep}")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+
+
+def test_tridel_interior_560k_triangles(rv, oracle_mod):
+    """f-1: the reference's large model (assets/models/tridel-interior-test.obj, 560 021
+    triangles, packed by tools/pack_tridel.py) through the library's own BVH builder and the
+    L2-resident traversal path: 640x360, frames 0..3 in one batched launch, every pixel against
+    the oracle; the per-bounce ray counts too."""
+    from rvpt_b200.scene import TRIDEL_NPZ
+    if not TRIDEL_NPZ.exists():
+        pytest.skip("rvpt_b200/assets/tridel_interior.npz not packed (tools/pack_tridel.py needs the reference tree)")
+    from conftest import PreparedScene
+    scene, pose, fov = rv.tridel_scene()
+    prep = PreparedScene(rv, scene)
+    assert len(prep.triangles) == 560021
+    W, H, N = 640, 360, 4
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    eng.render_frames(rv.default_settings(frame=0), cam, N)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    want = np.zeros(64, np.uint64)
+    for f in range(N):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+        want += ora.active
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "tridel interior, 4 frames")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    st = eng.stats()
+    got = np.zeros(64, np.uint64)
+    got[:len(st["active"])] = st["active"]
+    assert np.array_equal(got, want)
+    assert len(st["active"]) == 8 and st["active"][7] > 0, "an interior: paths live through all 8 bounces"

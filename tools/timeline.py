@@ -18,6 +18,9 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--flags", type=lambda v: int(v, 0), default=0)
 ap.add_argument("--frames", type=int, default=12)
+ap.add_argument("--batch", type=int, default=0, help="frames per batched launch (0: one launch per frame)")
+ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--nranks", type=int, default=1, help="render one rank's tile set of an N-way partition")
 args = ap.parse_args()
 
 scene = rv.builtin_scene() if args.scene == "builtin" else rv.cornell_scene()
@@ -27,21 +30,26 @@ if args.scene == "cornell":
     pose, fov = (0.0, 1.2, -3.4), 60.0
 W, H = args.width, args.height
 cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
-eng = rv.Engine(W, H, flags=args.flags)
+eng = rv.Engine(W, H, flags=args.flags, rank=args.rank, nranks=args.nranks)
 eng.upload(scene)
-eng.render_frames(rv.default_settings(frame=0), cam, 4)
+eng.render_frames(rv.default_settings(frame=0), cam, max(4, args.batch))
 eng.sync()
 eng.set_timeline(True)
 rows = []
 for f in range(4, 4 + args.frames):
-    eng.render_frame(rv.default_settings(frame=f), cam)
+    if args.batch:
+        eng.render_frames(rv.default_settings(frame=0), cam, args.batch)
+    else:
+        eng.render_frame(rv.default_settings(frame=f), cam)
     tl = eng.timeline().astype(np.int64)
     t0 = tl[:, 0].min()
     rel = np.where(tl > 0, tl - t0, -1) / 1e3  # us
     rows.append(rel)
 st = eng.stats()
-print(f"# frame-kernel timeline, {args.scene} scene, {W}x{H}, pose {pose}, flags {args.flags:#x}")
-print(f"active rays per bounce (last frame): {st['active']}")
+print(f"# frame-kernel timeline, {args.scene} scene, {W}x{H}, pose {pose}, flags {args.flags:#x}, "
+      f"{'one launch per frame' if not args.batch else str(args.batch) + ' frames per launch'}, "
+      f"rank {args.rank} of {args.nranks}")
+print(f"active rays per bounce (last launch, {st['frames']} frame(s)): {st['active']}")
 print()
 print("Per phase stamp, over CTAs (us since the first CTA entered the kernel), median over "
       f"{args.frames} frames of (min / median / max over CTAs):")
@@ -52,6 +60,8 @@ names = {0: "kernel entry", 1: "scene staged + copies derived", 2: "primary wave
 for b in range(1, 7):
     names[2 * b + 1] = f"past grid barrier before wave {b}"
     names[2 * b + 2] = f"wave {b} done (warp 0)"
+if args.batch:
+    names[14], names[15] = "every sample parked (past the barrier before the resolve)", "resolve phase done (warp 0)"
 for k in range(16):
     vals = [(r[:, k][r[:, k] >= 0]) for r in rows]
     if not all(len(v) for v in vals):
