@@ -11,15 +11,20 @@
 #define RVPT_TILE_DIM 16u          /* reference workgroup footprint, compute_pass.comp:27 */
 #define RVPT_TILE_PIXELS 256u
 #define RVPT_NODE_END 0xFFFFFFFFu  /* traversal finished */
-#define RVPT_NODE_INNER 0xFFFFFFFFu /* DevNode::leaf_first of an inner node */
+#define RVPT_NODE_INNER 0x80000000u /* DevNode::leaf_first of an inner node: this bit | index of its second child */
 #define RVPT_TRI_LAST 0x80000000u  /* meta bit: last triangle of its leaf */
 /* Binned path queues (closed scenes): a queue is RVPT_SORT_BINS sub-queues — one per direction
  * octant (3 bits) x origin cell (RVPT_SORT_CELL_BITS per axis of the scene's bounding box) —
  * of bin_cap entries each, plus one overflow / unsorted sub-queue that can hold every path. The
  * rays a warp of the next wave loads together (32 consecutive entries of one sub-queue) then walk
- * the same octant's node array from nearby origins. */
-#define RVPT_SORT_CELL_BITS 1u
-#define RVPT_SORT_BINS (8u << (3u * RVPT_SORT_CELL_BITS))       /* 64 */
+ * the same octant's node array. Measured on the Cornell box (profiles/r02_sort_experiments.md):
+ * octants alone (CELL_BITS 0) gain 9-12 %; adding 2x2x2 origin cells — which the lockstep model
+ * of tools/bvh_cost.py rated at -17 % per later wave — gains nothing there and doubles the
+ * primary wave's push time, so the default is 0. */
+#ifndef RVPT_SORT_CELL_BITS
+#define RVPT_SORT_CELL_BITS 0u
+#endif
+#define RVPT_SORT_BINS (8u << (3u * RVPT_SORT_CELL_BITS))       /* 8 */
 /* batched launches (render_frames): a queued path carries `slot | frame_in_batch << 26` */
 #define RVPT_BATCH_SLOT_BITS 26u
 #define RVPT_BATCH_SLOT_MASK ((1u << RVPT_BATCH_SLOT_BITS) - 1u)
@@ -40,7 +45,8 @@ struct DevNode
     float bmin_x, bmax_x, bmin_y, bmax_y; /* bounds[0..3] */
     float bmin_z, bmax_z;                 /* bounds[4..5] */
     uint32_t skip;                        /* next node when this subtree is done / missed */
-    uint32_t leaf_first;                  /* first DevTri of a leaf, RVPT_NODE_INNER otherwise */
+    uint32_t leaf_first;                  /* first DevTri of a leaf; inner node: RVPT_NODE_INNER | second child
+                                           * (the first child is node + 1) */
 };
 
 /*

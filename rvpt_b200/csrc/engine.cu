@@ -465,6 +465,7 @@ int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
             const uint32_t c0 = k + 1;
             const uint32_t c1 = c0 + size[c0];
             size[k] = 1 + size[c0] + size[c1];
+            out.nodes[k].leaf_first = RVPT_NODE_INNER | c1;
         }
         const uint32_t next = k + size[k];
         out.nodes[k].skip = next < total ? next : RVPT_NODE_END;
@@ -592,7 +593,7 @@ void build_octant_layouts(const std::vector<DevNode>& ref, std::vector<float>& o
             std::memcpy(&b[2], &skip, 4);
             std::memcpy(&b[3], &d.leaf_first, 4);
             ++idx;
-            if (d.leaf_first == RVPT_NODE_INNER)
+            if (d.leaf_first & RVPT_NODE_INNER)
             {
                 const uint32_t c0 = k + 1u, c1 = c0 + size_of(c0);
                 const DevNode &p = ref[c0], &q = ref[c1];

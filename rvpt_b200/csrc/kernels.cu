@@ -239,17 +239,22 @@ __device__ __forceinline__ SceneViewT<kSmem> make_view(const unsigned char* base
  * a leaf box whose slab entry rounds above closest_t is culled even if its triangle's plane t
  * rounds below it) when a SECOND accepted triangle lies within rounding distance of the nearest
  * one: a shared edge, a corner, crossing surfaces. Such walks therefore run RELAXED, at no extra
- * instruction in the node or plane tests: the loop carries clip_t = closest_t * (1 + 3 * 2^-12)
- * instead of closest_t — boxes and plane tests are clipped against it, so every triangle within
- * the band of the nearest one is seen — and an accepted triangle that finds or leaves another one
- * inside the band flags the hit AMBIGUOUS (top bit of the triangle index). trace_nearest()
- * re-traces flagged rays (about one in a million) with the reference's own walk, and recomputes
- * the exact t of the others from the winning triangle (same operations, same bits). The band is
- * far above the rounding error of t (a few ulp; more at grazing incidence) and far below any
- * geometric separation. Found by the full-size parity runs of round 2: without it, 2 of 1.3e8
- * samples of the pinned pose and 1 of 3.3e7 of the Cornell box picked another triangle. */
-#define RVPT_TIE_BAND 1.000732421875f  /* 1 + 3 * 2^-12 */
+ * instruction in the node or plane tests and no extra register: the loop carries the CLIP
+ * distance — closest_t moved up by RVPT_TIE_ULPS units in the last place (its bit pattern plus
+ * a constant: monotonic, exactly invertible; 3.7e-4 to 7.3e-4 relative) — instead of closest_t.
+ * Boxes and plane tests are clipped against it, so every triangle within the band of the nearest
+ * one is seen, and an accepted triangle that finds or leaves another one inside the band flags
+ * the hit AMBIGUOUS (top bit of the triangle index). trace_nearest() re-traces flagged rays
+ * (about one in a million) with the reference's own walk and recovers the exact t of the others
+ * by subtracting the constant again. The band is far above the rounding error of t (a few ulp;
+ * more at grazing incidence) and far below any geometric separation. Found by the full-size
+ * parity runs of round 2: without it, 2 of 1.3e8 samples of the pinned pose and 1 of 3.3e7 of
+ * the Cornell box picked another triangle than the reference's walk. */
+#define RVPT_TIE_ULPS 6144 /* 3 * 2^11 ulp = 3 * 2^-12 relative at the bottom of a binade */
 #define RVPT_TRI_AMBIGUOUS 0x80000000u
+
+__device__ __forceinline__ float clip_of(float t) { return __int_as_float(__float_as_int(t) + RVPT_TIE_ULPS); }
+__device__ __forceinline__ float exact_of(float clip) { return __int_as_float(__float_as_int(clip) - RVPT_TIE_ULPS); }
 
 __device__ __forceinline__ bool hit_is_ambiguous(uint32_t best_tri)
 {
@@ -258,7 +263,7 @@ __device__ __forceinline__ bool hit_is_ambiguous(uint32_t best_tri)
 
 /* Leaf: intersect_triangle_fast (intersection.glsl:267-323) on the precomputed
  * records of one leaf; the early-out after the plane test is value-neutral
- * because the acceptance test is a pure conjunction. kRelaxed: best_t is clip_t (see above). */
+ * because the acceptance test is a pure conjunction. kRelaxed: best_t is the clip distance. */
 template <bool kSmem, bool kRel, bool kRelaxed>
 __device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d, uint32_t i,
                                           float& best_t, uint32_t& best_tri)
@@ -290,11 +295,11 @@ __device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, 
             {
                 if constexpr (kRelaxed)
                 {
-                    const float tc = t * RVPT_TIE_BAND;
+                    const float tc = clip_of(t); /* t is finite and positive here */
                     if (tc < best_t)
                     {
                         /* new nearest; the previous one may still lie inside its band */
-                        best_tri = (best_t <= tc * RVPT_TIE_BAND) ? (i | RVPT_TRI_AMBIGUOUS) : i;
+                        best_tri = (best_t <= clip_of(tc)) ? (i | RVPT_TRI_AMBIGUOUS) : i;
                         best_t = tc;
                     }
                     else
@@ -323,8 +328,12 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
                                              uint32_t& best_tri)
 {
     /* the octant arrays may be in front-to-back order: relaxed walk, best_t is the clip
-     * distance closest_t * RVPT_TIE_BAND until trace_nearest() recomputes the exact t */
+     * distance until trace_nearest() turns it back into the exact t */
+#ifdef RVPT_PROBE_NO_RELAXED
+    constexpr bool kRelaxed = false; /* timing probe only: front-to-back results are not exact */
+#else
     constexpr bool kRelaxed = kSorted;
+#endif
     uint32_t node = 0;
     while (node != RVPT_NODE_END)
     {
@@ -339,6 +348,15 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
         {
             n0 = ld_f4<kSmem>(nodes, 2 * node);
             n1 = ld_f4<kSmem>(nodes, 2 * node + 1);
+            if constexpr (!kSmem)
+            {
+                /* large scenes are bound by one L2 round trip per node: the first child is the
+                 * next record (same or next cache line), the skip target is anywhere — start
+                 * fetching it while the slab test decides */
+                const uint32_t sk = __float_as_uint(n1.z);
+                if (sk != RVPT_NODE_END)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(nodes) + 2 * (size_t)sk));
+            }
         }
         float fx, nx, fy, ny, fz, nz;
         if (kRel)
@@ -370,7 +388,7 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
         const uint32_t leaf = __float_as_uint(n1.w);
         if (t1 >= t0)
         {
-            if (leaf != RVPT_NODE_INNER)
+            if (!(leaf & RVPT_NODE_INNER))
             {
                 test_leaf<kSmem, kRel, kRelaxed>(sc, o, d, leaf, best_t, best_tri);
                 node = skip;
@@ -386,8 +404,7 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
 /* The reference's walk for the rare ray whose front-to-back result is ambiguous. Out of line
  * on purpose: one copy per kernel, and its registers are not the hot loops' problem. Shared-
  * memory scenes only (the global path always walks the reference's order). */
-__device__ __noinline__ void retrace_reference_order(uint32_t nodes, uint32_t tris, uint32_t meta, rv_f3 o,
-                                                     rv_f3 d, float* best_t, uint32_t* best_tri)
+__device__ __noinline__ uint2 retrace_reference_order(uint32_t nodes, uint32_t tris, uint32_t meta, rv_f3 o, rv_f3 d)
 {
     SceneViewT<true> sc;
     sc.nodes = nodes, sc.tris = tris, sc.meta = meta, sc.mats = 0;
@@ -397,8 +414,7 @@ __device__ __noinline__ void retrace_reference_order(uint32_t nodes, uint32_t tr
     float t = RV_INF;
     uint32_t tri = 0xFFFFFFFFu;
     walk_nearest<true, false, false>(sc, sc.nodes, o, d, ix, iy, iz, t, tri);
-    *best_t = t;
-    *best_tri = tri;
+    return make_uint2(__float_as_uint(t), tri);
 }
 
 template <bool kSmem, bool kRel, bool kOct>
@@ -425,26 +441,23 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
             /* opaque to ptxas, which otherwise re-derives this address (shared window base,
              * constant-bank loads, octant bits) inside the node loop to save a register */
             asm volatile("" : "+r"(base));
+#ifdef RVPT_PROBE_NO_RELAXED
+            walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+#else
             walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
             if (best_tri != 0xFFFFFFFFu)
             {
-#ifndef RVPT_PROBE_NO_RETRACE
                 if (hit_is_ambiguous(best_tri))
                     /* a runner-up within rounding distance of the nearest hit: the reference's own
                      * walk decides (plain node array, reference child order, exact clipping) */
-                    retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d, &best_t, &best_tri);
-                else
-#endif
                 {
-                    /* the relaxed walk carried the clip distance: the hit's t, recomputed with the
-                     * operations of the plane test (same inputs, same bits) */
-                    const float4 A = ld_f4<kSmem>(sc.tris, 4 * best_tri + 0);
-                    const float4 B = ld_f4<kSmem>(sc.tris, 4 * best_tri + 1);
-                    const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, best_tri))
-                                           : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
-                    best_t = num / rv_dot(d, rv_make(B.x, B.y, B.z));
+                    const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d);
+                    best_t = __uint_as_float(r.x), best_tri = r.y;
                 }
+                else
+                    best_t = exact_of(best_t);
             }
+#endif
         }
         else
             walk_nearest<kSmem, false, false>(sc, sc.nodes, o, d, ix, iy, iz, best_t, best_tri);
@@ -1537,7 +1550,7 @@ __device__ __forceinline__ bool trace_any(const SceneViewT<kSmem>& sc, rv_f3 o, 
         const uint32_t leaf = __float_as_uint(n1.w);
         if (t1 >= t0)
         {
-            if (leaf != RVPT_NODE_INNER)
+            if (!(leaf & RVPT_NODE_INNER))
             {
                 uint32_t i = leaf, m;
                 do

@@ -262,12 +262,13 @@ def test_front_to_back_octant_layouts(rv, scene_name):
                           lo(A[k, :, 2], A[k, :, 3], sy), hi(A[k, :, 2], A[k, :, 3], sy),
                           lo(B[k, :, 0], B[k, :, 1], sz), hi(B[k, :, 0], B[k, :, 1], sz)], 1)
         assert sorted(tuple(float(v) for v in r) for r in boxes) == ref_boxes
-        assert int((leaf != END).sum()) == n_leaves
+        is_leaf = (leaf & 0x80000000) == 0  # inner records carry RVPT_NODE_INNER | second child
+        assert int(is_leaf.sum()) == n_leaves
         # pre-order consistency: an inner node's first child is the next record; the second child starts
         # where the first child's subtree ends; a subtree's skip is its parent's second child or skip
         def check(i, end):
             assert (skip[i] == END and end == n) or skip[i] == end, (k, i)
-            if leaf[i] != END:
+            if is_leaf[i]:
                 return i + 1
             c0 = i + 1
             c1 = int(skip[c0]) if skip[c0] != END else n
@@ -283,8 +284,8 @@ def test_front_to_back_octant_layouts(rv, scene_name):
         sys.setrecursionlimit(10000)
         check(0, n)
         # every leaf's triangle range appears exactly once
-        assert sorted(leaf[leaf != END].tolist()) == sorted(
-            set(leaf[leaf != END].tolist())), "leaf ranges must be distinct"
+        assert sorted(leaf[is_leaf].tolist()) == sorted(
+            set(leaf[is_leaf].tolist())), "leaf ranges must be distinct"
 
 
 def test_coincident_face_detection(rv):

@@ -80,8 +80,8 @@ def front_to_back_layouts(nodes, tris):
         skip_u = B[k, :, 2].copy().view(np.uint32).astype(np.int64)
         skip = np.where(skip_u == 0xFFFFFFFF, END, skip_u)
         leaf_u = B[k, :, 3].copy().view(np.uint32).astype(np.int64)
-        first = np.array([count_of[int(v)][0] if v != 0xFFFFFFFF else -1 for v in leaf_u])
-        cnt = np.array([count_of[int(v)][1] if v != 0xFFFFFFFF else 0 for v in leaf_u])
+        first = np.array([count_of[int(v)][0] if not (v & 0x80000000) else -1 for v in leaf_u])
+        cnt = np.array([count_of[int(v)][1] if not (v & 0x80000000) else 0 for v in leaf_u])
         layouts.append((bounds.astype(np.float32), skip, first, cnt))
     return layouts
 
