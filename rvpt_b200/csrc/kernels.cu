@@ -348,15 +348,6 @@ __device__ __forceinline__ void walk_nearest(const SceneViewT<kSmem>& sc,
         {
             n0 = ld_f4<kSmem>(nodes, 2 * node);
             n1 = ld_f4<kSmem>(nodes, 2 * node + 1);
-            if constexpr (!kSmem)
-            {
-                /* large scenes are bound by one L2 round trip per node: the first child is the
-                 * next record (same or next cache line), the skip target is anywhere — start
-                 * fetching it while the slab test decides */
-                const uint32_t sk = __float_as_uint(n1.z);
-                if (sk != RVPT_NODE_END)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(nodes) + 2 * (size_t)sk));
-            }
         }
         float fx, nx, fy, ny, fz, nz;
         if (kRel)

@@ -1,24 +1,23 @@
 #!/bin/bash
-# strong-scaling run on one box: N = 1, 2, 4, 8 (subset of the visible GPUs), p2p fused output
+# bench.py at N GPUs of one box, launched the way the driver launches it. usage: gpu_scale.sh <tag> <N...>
 mkdir -p gpurun_out
-TAG=${1:-r01}
-for n in 1 2 4 8; do
-  if [ $n -eq 1 ]; then timeout 200 python bench.py --steps 100 > gpurun_out/scale_${TAG}_n$n.json 2>gpurun_out/scale_${TAG}_n$n.err;
-  else timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 100 > gpurun_out/scale_${TAG}_n$n.json 2>gpurun_out/scale_${TAG}_n$n.err; fi
-  grep -iE "error|Traceback" gpurun_out/scale_${TAG}_n$n.err | head -3
-  python - <<PY
-import json
-l=[x for x in open('gpurun_out/scale_${TAG}_n$n.json') if x.startswith('{')]
-d=json.loads(l[-1]); print('N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'us/frame', round(d['ms_per_step']/d['config']['frames_per_step']*1000,1), '|', d['config']['gather'][:30], '|', d['config']['launch'][:30], d['clocks'])
+TAG=${1:-scale}; shift
+for N in "$@"; do
+  if [ "$N" = "1" ]; then
+    timeout 900 python bench.py --gpus 1 > gpurun_out/bench_${TAG}_n1.json 2> gpurun_out/bench_${TAG}_n1.err
+  else
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N > gpurun_out/bench_${TAG}_n$N.json 2> gpurun_out/bench_${TAG}_n$N.err
+  fi
+  python - "$TAG" "$N" <<'PY'
+import json, sys
+try:
+    lines = [l for l in open("gpurun_out/bench_%s_n%s.json" % (sys.argv[1], sys.argv[2])) if l.startswith("{")]
+    d = json.loads(lines[-1])
+    print("N", sys.argv[2], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "parity", d["parity_ok"], "ms/step", round(d["ms_per_step"], 3),
+          "c4", d["c4"] and (round(d["c4"]["value"]), d["c4"]["parity_ok"], round(d["c4"]["ms_per_step"], 3)), "launches", d["gpu_launches"], d["run"]["launch"][:60])
+except Exception as e:
+    print("N", sys.argv[2], "failed", e)
 PY
-done
-# C4: 3840x2160, 16 spp, 8 GPUs vs 1 GPU
-for n in 1 8; do
-  if [ $n -eq 1 ]; then timeout 200 python bench.py --steps 30 --width 3840 --height 2160 --no-cpu-baseline > gpurun_out/c4_${TAG}_n$n.json 2>gpurun_out/c4_${TAG}_n$n.err;
-  else timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 30 --width 3840 --height 2160 > gpurun_out/c4_${TAG}_n$n.json 2>gpurun_out/c4_${TAG}_n$n.err; fi
-  python - <<PY
-import json
-l=[x for x in open('gpurun_out/c4_${TAG}_n$n.json') if x.startswith('{')]
-d=json.loads(l[-1]); print('C4 4K N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'us/frame', round(d['ms_per_step']/d['config']['frames_per_step']*1000,1))
-PY
+  tail -2 gpurun_out/bench_${TAG}_n$N.err | cut -c1-300
 done
