@@ -316,6 +316,21 @@ RVPT_API int rvpt_b200_export_output(rvpt_b200_ctx* ctx, unsigned char handle[64
  * image and write this rank's pixels into it. */
 RVPT_API int rvpt_b200_attach_output(rvpt_b200_ctx* ctx, const unsigned char handle[64]);
 
+/* Double-buffered result image: the read-back of one step overlaps the frames of the next.
+ * read_output_rgba8_async() enqueues the device -> host copy of the image the last frames wrote
+ * (dst should be pinned host memory) on an internal copy stream, behind those frames, and
+ * returns at once; frames launched afterwards fill the ctx's SECOND raster image, so nothing
+ * overwrites the one in flight. wait_output() blocks until the last such copy has landed.
+ * Needs a ctx that owns the raster image (one GPU, or the display rank). With the fused
+ * multi-GPU gather the display rank exports both images (export_output + export_output2), the
+ * other ranks attach both (attach_output + attach_output2) and call flip_output() once per
+ * step, in step with the display rank's read_output_rgba8_async(). */
+RVPT_API int rvpt_b200_read_output_rgba8_async(rvpt_b200_ctx* ctx, uint8_t* dst);
+RVPT_API int rvpt_b200_wait_output(rvpt_b200_ctx* ctx);
+RVPT_API int rvpt_b200_flip_output(rvpt_b200_ctx* ctx);
+RVPT_API int rvpt_b200_export_output2(rvpt_b200_ctx* ctx, unsigned char handle[64]);
+RVPT_API int rvpt_b200_attach_output2(rvpt_b200_ctx* ctx, const unsigned char handle[64]);
+
 /* ------------------------------------------------------------------------ */
 /* Host-side utilities (no GPU needed).                                      */
 /* ------------------------------------------------------------------------ */

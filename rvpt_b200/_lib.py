@@ -86,6 +86,11 @@ SIGNATURES = {
                                       C.c_void_p]),
     "rvpt_b200_export_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_attach_output": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvpt_b200_read_output_rgba8_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvpt_b200_wait_output": (C.c_int, [C.c_void_p]),
+    "rvpt_b200_flip_output": (C.c_int, [C.c_void_p]),
+    "rvpt_b200_export_output2": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvpt_b200_attach_output2": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_build_bvh": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
                                       C.c_void_p]),
     "rvpt_b200_camera_data": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,

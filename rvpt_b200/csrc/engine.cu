@@ -75,8 +75,19 @@ struct rvpt_b200_ctx
     void* d_out_tiles = nullptr;  /* own allocation */
     void* accum = nullptr;        /* in use (own or external) */
     void* out_tiles = nullptr;
-    uchar4* d_out_raster = nullptr; /* nranks == 1, or exported by the display rank */
-    uchar4* peer_out_raster = nullptr; /* display rank's image, mapped through CUDA IPC */
+    /* The raster result image exists twice ("front" / "back", the second one on demand) so that an
+     * asynchronous read-back of one can overlap the frames that fill the other
+     * (rvpt_b200_read_output_rgba8_async / flip_output). [0] is the image every other entry point
+     * means. */
+    uchar4* d_out_raster = nullptr;  /* [out_cur == 0]: nranks == 1, or exported by the display rank */
+    uchar4* d_out_raster2 = nullptr; /* [out_cur == 1] */
+    uchar4* peer_out_raster = nullptr;  /* display rank's images, mapped through CUDA IPC */
+    uchar4* peer_out_raster2 = nullptr;
+    int out_cur = 0;  /* image the next frames write */
+    int out_last = 0; /* image the last frames wrote (what read_output_rgba8 returns) */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;
     float4* d_carry = nullptr;      /* allocated on first aa > 1 */
     float4* d_samples = nullptr;    /* batched launches: [batch_cap][slots] parked samples */
     PathQueue queue[2]{};
@@ -159,6 +170,7 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
     cudaFree(ctx->d_accum);
     cudaFree(ctx->d_out_tiles);
     cudaFree(ctx->d_out_raster);
+    cudaFree(ctx->d_out_raster2);
     cudaFree(ctx->d_carry);
     cudaFree(ctx->d_ctr);
     cudaFree(ctx->d_scratch);
@@ -166,6 +178,7 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
     ctx->d_accum = ctx->d_out_tiles = nullptr;
     ctx->accum = ctx->out_tiles = nullptr;
     ctx->d_out_raster = nullptr;
+    ctx->d_out_raster2 = nullptr;
     ctx->d_carry = nullptr;
     ctx->d_ctr = nullptr;
     ctx->d_scratch = nullptr;
@@ -826,6 +839,14 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->peer_out_raster) cudaIpcCloseMemHandle(ctx->peer_out_raster);
+        if (ctx->peer_out_raster2) cudaIpcCloseMemHandle(ctx->peer_out_raster2);
+        if (ctx->copy_stream)
+        {
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamDestroy(ctx->copy_stream);
+            cudaEventDestroy(ctx->ev_rendered);
+            cudaEventDestroy(ctx->ev_copied);
+        }
         free_frame_buffers(ctx);
         cudaFree(ctx->d_timeline);
         cudaFree(ctx->d_scene);
@@ -990,7 +1011,11 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.accum_u8 = (ctx->flags & RVPT_B200_FLAG_ACCUM_RGBA8) ? (uchar4*)ctx->accum : nullptr;
     p.out_tiles = (uchar4*)ctx->out_tiles;
     /* raster target: the display rank's image over NVLink, else our own */
-    p.out_raster = ctx->peer_out_raster ? ctx->peer_out_raster : ctx->d_out_raster;
+    if (ctx->out_cur == 0)
+        p.out_raster = ctx->peer_out_raster ? ctx->peer_out_raster : ctx->d_out_raster;
+    else
+        p.out_raster = ctx->peer_out_raster2 ? ctx->peer_out_raster2 : ctx->d_out_raster2;
+    ctx->out_last = ctx->out_cur;
     p.carry = ctx->d_carry;
     p.ctr = ctx->d_ctr;
     p.timeline = ctx->d_timeline;
@@ -1151,7 +1176,8 @@ extern "C" int rvpt_b200_read_output_rgba8(rvpt_b200_ctx* ctx, uint8_t* dst)
     const size_t bytes = (size_t)ctx->W * ctx->H * 4;
     if (ctx->d_out_raster && !ctx->peer_out_raster)
     {
-        CU(cudaMemcpyAsync(dst, ctx->d_out_raster, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        const uchar4* src = (ctx->out_last == 1 && ctx->d_out_raster2) ? ctx->d_out_raster2 : ctx->d_out_raster;
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     else
     {
@@ -1230,6 +1256,8 @@ extern "C" int rvpt_b200_reset_accum(rvpt_b200_ctx* ctx)
     CU(cudaMemsetAsync(ctx->out_tiles, 0, slots * 4, ctx->stream));
     if (ctx->d_out_raster)
         CU(cudaMemsetAsync(ctx->d_out_raster, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+    if (ctx->d_out_raster2)
+        CU(cudaMemsetAsync(ctx->d_out_raster2, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
     return 0;
 }
 
@@ -1398,6 +1426,100 @@ extern "C" int rvpt_b200_attach_output(rvpt_b200_ctx* ctx, const unsigned char h
     void* ptr = nullptr;
     CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_out_raster = (uchar4*)ptr;
+    return 0;
+}
+
+namespace
+{
+int ensure_second_image(rvpt_b200_ctx* ctx)
+{
+    if (ctx->d_out_raster2) return 0;
+    if (!ctx->d_out_raster) return fail(ctx, RVPT_B200_EINVAL, "this ctx owns no raster result image");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(&ctx->d_out_raster2, (size_t)ctx->W * ctx->H * 4));
+    CU(cudaMemsetAsync(ctx->d_out_raster2, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+} /* namespace */
+
+extern "C" int rvpt_b200_export_output2(rvpt_b200_ctx* ctx, unsigned char handle[64])
+{
+    if (!ctx || !handle) return RVPT_B200_EINVAL;
+    unsigned char first[64];
+    int rc = rvpt_b200_export_output(ctx, first); /* makes sure the first image exists */
+    if (rc) return rc;
+    if ((rc = ensure_second_image(ctx))) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_out_raster2));
+    std::memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int rvpt_b200_attach_output2(rvpt_b200_ctx* ctx, const unsigned char handle[64])
+{
+    if (!ctx || !handle) return RVPT_B200_EINVAL;
+    if (!ctx->peer_out_raster) return fail(ctx, RVPT_B200_EINVAL, "attach_output must precede attach_output2");
+    if (ctx->peer_out_raster2) return fail(ctx, RVPT_B200_EINVAL, "a second output image is already attached");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_out_raster2 = (uchar4*)ptr;
+    return 0;
+}
+
+extern "C" int rvpt_b200_flip_output(rvpt_b200_ctx* ctx)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    if (ctx->peer_out_raster)
+    {
+        if (!ctx->peer_out_raster2) return fail(ctx, RVPT_B200_EINVAL, "flip_output needs attach_output2 on an attached ctx");
+    }
+    else if ((rc = ensure_second_image(ctx)))
+        return rc;
+    ctx->out_cur ^= 1;
+    return 0;
+}
+
+extern "C" int rvpt_b200_read_output_rgba8_async(rvpt_b200_ctx* ctx, uint8_t* dst)
+{
+    if (!ctx || !dst) return RVPT_B200_EINVAL;
+    int rc = ensure_frame_buffers(ctx);
+    if (rc) return rc;
+    if (!ctx->d_out_raster || ctx->peer_out_raster)
+        return fail(ctx, RVPT_B200_EINVAL, "read_output_rgba8_async needs a ctx that owns the raster image "
+                                           "(one GPU, or the display rank after export_output)");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream)
+    {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_rendered, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    }
+    if ((rc = ensure_second_image(ctx))) return rc;
+    /* the frames launched from now on must not start before the previous copy has left the image
+     * they are about to overwrite (it is the one that copy read) */
+    if (ctx->copy_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+    const uchar4* src = ctx->out_last == 1 ? ctx->d_out_raster2 : ctx->d_out_raster;
+    CU(cudaEventRecord(ctx->ev_rendered, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered, 0));
+    CU(cudaMemcpyAsync(dst, src, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    ctx->copy_pending = true;
+    ctx->out_cur = ctx->out_last ^ 1; /* later frames fill the other image */
+    return 0;
+}
+
+extern "C" int rvpt_b200_wait_output(rvpt_b200_ctx* ctx)
+{
+    if (!ctx) return RVPT_B200_EINVAL;
+    if (!ctx->copy_pending) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_copied));
     return 0;
 }
 

@@ -119,18 +119,35 @@ class PeerOutput:
     def __init__(self, engine, dist, torch, device):
         self.engine, self.dist, self.torch = engine, dist, torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        handle = torch.zeros(64, dtype=torch.uint8, device=device)
-        if self.rank == 0:
-            handle.copy_(torch.frombuffer(bytearray(engine.export_output()), dtype=torch.uint8))
-        dist.broadcast(handle, src=0)
-        if self.rank != 0:
-            engine.attach_output(bytes(handle.cpu().numpy().tobytes()))
+        # both images of the display rank's double-buffered result (see read_image_async)
+        for second in (False, True):
+            handle = torch.zeros(64, dtype=torch.uint8, device=device)
+            if self.rank == 0:
+                handle.copy_(torch.frombuffer(bytearray(engine.export_output(second)), dtype=torch.uint8))
+            dist.broadcast(handle, src=0)
+            if self.rank != 0:
+                engine.attach_output(bytes(handle.cpu().numpy().tobytes()), second)
         dist.barrier()
 
     def finish(self) -> None:
         """Every rank's frames have landed in rank 0's image after this."""
         self.torch.cuda.synchronize()
         self.dist.barrier()
+
+    def read_image_async(self, out_pinned: np.ndarray) -> None:
+        """End of a step with the read-back overlapping the next step: every rank's pixels are in
+        the display rank's current image (stream completion + barrier); the display rank starts
+        copying it to `out_pinned` and every rank switches to the other image for what it renders
+        next. engine.wait_output() on rank 0 (before the buffer is reused) completes the copy."""
+        if self.rank == 0:
+            # the copy started one step ago read the image every rank is about to switch back to:
+            # it must have landed before the barrier lets them (it overlapped this step's frames)
+            self.engine.wait_output()
+        self.finish()
+        if self.rank == 0:
+            self.engine.read_output_rgba8_async(out_pinned)
+        else:
+            self.engine.flip_output()
 
     def image(self) -> np.ndarray:
         self.finish()

@@ -154,6 +154,18 @@ class Engine:
         self._check(self._lib.rvpt_b200_read_output_rgba8(self._ctx, out.ctypes.data))
         return out
 
+    def read_output_rgba8_async(self, out: np.ndarray) -> None:
+        """Enqueues the read-back of the last frames' image into `out` (pinned host memory, HxWx4
+        uint8) and returns; later frames fill the second image. Pair with wait_output()."""
+        assert out.nbytes == self.height * self.width * 4
+        self._check(self._lib.rvpt_b200_read_output_rgba8_async(self._ctx, out.ctypes.data))
+
+    def wait_output(self) -> None:
+        self._check(self._lib.rvpt_b200_wait_output(self._ctx))
+
+    def flip_output(self) -> None:
+        self._check(self._lib.rvpt_b200_flip_output(self._ctx))
+
     def read_accum_f32(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), np.float32)
         self._check(self._lib.rvpt_b200_read_accum_f32(self._ctx, out.ctypes.data))
@@ -208,17 +220,19 @@ class Engine:
     def set_external_tiles(self, d_accum: int | None, d_rgba8: int | None) -> None:
         self._check(self._lib.rvpt_b200_set_external_tiles(self._ctx, d_accum, d_rgba8))
 
-    def export_output(self) -> bytes:
-        """Display rank: CUDA IPC handle of the raster result image."""
+    def export_output(self, second: bool = False) -> bytes:
+        """Display rank: CUDA IPC handle of the raster result image (or of its double buffer)."""
         buf = (C.c_ubyte * 64)()
-        self._check(self._lib.rvpt_b200_export_output(self._ctx, buf))
+        fn = self._lib.rvpt_b200_export_output2 if second else self._lib.rvpt_b200_export_output
+        self._check(fn(self._ctx, buf))
         return bytes(buf)
 
-    def attach_output(self, handle: bytes) -> None:
+    def attach_output(self, handle: bytes, second: bool = False) -> None:
         """Other ranks: write finished pixels straight into the display rank's image."""
         assert len(handle) == 64
         buf = (C.c_ubyte * 64).from_buffer_copy(handle)
-        self._check(self._lib.rvpt_b200_attach_output(self._ctx, buf))
+        fn = self._lib.rvpt_b200_attach_output2 if second else self._lib.rvpt_b200_attach_output
+        self._check(fn(self._ctx, buf))
 
     def untile(self, d_gathered: int, d_raster: int, elem_bytes: int,
                cuda_stream: int | None = None) -> None:

@@ -828,3 +828,32 @@ def test_tridel_interior_560k_triangles(rv, oracle_mod):
     got[:len(st["active"])] = st["active"]
     assert np.array_equal(got, want)
     assert len(st["active"]) == 8 and st["active"][7] > 0, "an interior: paths live through all 8 bounces"
+
+
+def test_async_double_buffered_readback(rv, oracle_mod, builtin):
+    """rvpt_b200_read_output_rgba8_async: the copy of one step's image overlaps the frames of the
+    next, which fill the second raster image — both copies arrive intact, in any interleaving with
+    the synchronous read."""
+    torch = pytest.importorskip("torch")
+    W, H = 640, 360
+    cam = rv.camera_data(translation=DEFAULT_POSE, aspect=W / H)
+    want = {}
+    for n in (3, 8):
+        ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+        for f in range(n):
+            ora.render_frame(rv.default_settings(frame=f), cam)
+        want[n] = ora.result.copy()
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    bufs = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+    for rep in range(3):
+        eng.render_frames(rv.default_settings(frame=0), cam, 3)
+        eng.wait_output()
+        eng.read_output_rgba8_async(bufs[0])
+        eng.render_frames(rv.default_settings(frame=0), cam, 8)      # fills the other image meanwhile
+        assert np.array_equal(eng.read_output_rgba8(), want[8])     # synchronous read: the latest frames
+        eng.read_output_rgba8_async(bufs[1])
+        eng.wait_output()
+        assert np.array_equal(bufs[0], want[3]), f"first copy, repetition {rep}"
+        assert np.array_equal(bufs[1], want[8]), f"second copy, repetition {rep}"
+    eng.close()
