@@ -4,9 +4,10 @@ small tracked summaries under profiles/.
     python tools/summarize_profile.py <tag>     # e.g. r01
 
 Inputs : gpurun_out/launches_<tag>.csv, gpurun_out/prof_frame_<tag>.ncu-rep,
-         gpurun_out/bench_<tag>_n1.json
+         gpurun_out/bench_<tag>_*.json, gpurun_out/timeline_<tag>_*.md, gpurun_out/<tag>_sanitizer_*.log
 Outputs: profiles/<tag>_launches.md, profiles/<tag>_k_frame_metrics.md,
-         profiles/<tag>_k_frame_hot_blocks.txt, profiles/<tag>_bench_n1.json
+         profiles/<tag>_k_frame_hot_blocks.txt, profiles/k_frame_traffic.json, copies of the bench lines,
+         timelines and sanitizer summaries
 """
 import collections
 import csv
@@ -19,7 +20,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "gpurun_out"
 PROF = ROOT / "profiles"
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+PROFILE_CMD = "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c4 --no-parity"
 PROF.mkdir(exist_ok=True)
 
 # ---- launch list -----------------------------------------------------------------
@@ -33,7 +35,8 @@ for row in csv.DictReader(lines):
 total = sum(sum(v) for v in agg.values())
 with open(PROF / f"{tag}_launches.md", "w") as f:
     f.write(f"# ncu launch list ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over "
-            "`python bench.py --steps 1 --warmup 3 --frames 4 --no-cpu-baseline --graph off`.\n"
+            f"`{PROFILE_CMD}` (64-frame steps: one batched `k_frame` launch each; the other kernels are "
+            "torch's L2-flush memset and the roofline / e2e passes of bench.py).\n"
             "Per-launch times are cold-cache and serialised: compare shares, not absolutes.\n\n"
             "| kernel | launches | mean us | min us | max us | share of device time |\n|---|---|---|---|---|---|\n")
     for k, v in agg.items():
@@ -57,8 +60,9 @@ want = [
     "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 with open(PROF / f"{tag}_k_frame_metrics.md", "w") as f:
-    f.write(f"# k_frame, `ncu --set full --clock-control none` ({tag})\n\n"
-            "Workload: C2 (built-in scene, default pose, 1920x1080, 8 bounces, aa 1). One column per captured launch.\n\n"
+    f.write(f"# k_frame (batched, 64 frames per launch), `ncu --set full --clock-control none` ({tag})\n\n"
+            "Workload: C2 (built-in scene, default pose, 1920x1080, 8 bounces, aa 1, frames 0..63 in one launch). "
+            "One column per captured launch.\n\n"
             "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(vals))) + " |\n|---|---|" + "---|" * len(vals) + "\n")
     for k in want:
         if k in hdr:
@@ -81,11 +85,11 @@ def _bytes(name):
 
 rd, wr = _bytes("dram__bytes_read.sum"), _bytes("dram__bytes_write.sum")
 (PROF / "k_frame_traffic.json").write_text(json.dumps({
-    "tag": tag, "kernel": "k_frame", "launches_captured": len(vals),
+    "tag": tag, "kernel": "k_frame<batched>", "launches_captured": len(vals), "frames_per_launch": 64,
     "dram_bytes_per_launch": sum(rd + wr) / len(vals),
     "dram_bytes_read": rd, "dram_bytes_write": wr,
     "source": f"ncu --set full --clock-control none, gpurun_out/prof_frame_{tag}.ncu-rep "
-              "(python bench.py --steps 1 --warmup 3 --frames 4 --no-cpu-baseline --graph off)"}, indent=1) + "\n")
+              f"({PROFILE_CMD})"}, indent=1) + "\n")
 
 src = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
 (OUT / f"src_{tag}.csv").write_text(src)
@@ -95,7 +99,14 @@ blocks = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_blocks.py"), 
     "SASS basic-block groups of k_frame with >= 1% of executed warp-instructions\n"
     "(start-end SASS index, instructions in block, executions, share of instructions, share of stall samples,\n"
     " avg active threads, top opcodes). The 27-instruction FMNMX/FMUL/LDS blocks are the BVH node slab test.\n\n" + blocks)
-for name in (f"bench_{tag}_n1.json", f"bench_{tag}_pinned.json"):
-    if (OUT / name).exists():
-        shutil.copy(OUT / name, PROF / name.replace("bench_", f"").replace(f"{tag}_", f"{tag}_bench_"))
+for src in sorted(OUT.glob(f"bench_{tag}_*.json")):
+    lines = [l for l in src.read_text().splitlines() if l.startswith("{")]
+    if lines:
+        (PROF / src.name.replace(f"bench_{tag}_", f"{tag}_bench_")).write_text(lines[-1] + "\n")
+for src in sorted(OUT.glob(f"timeline_{tag}_*.md")):
+    shutil.copy(src, PROF / src.name.replace(f"timeline_{tag}_", f"{tag}_timeline_"))
+for src in sorted(OUT.glob(f"{tag}_sanitizer_*.log")):
+    text = src.read_text().splitlines()
+    keep = [l for l in text if "SUMMARY" in l or "ERROR" in l or "smoke ok" in l or "batch ok" in l][-12:]
+    (PROF / src.name).write_text("\n".join(keep) + "\n")
 print("wrote", sorted(p.name for p in PROF.glob(f"{tag}_*")))
