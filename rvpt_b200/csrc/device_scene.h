@@ -169,6 +169,10 @@ struct FrameParams
     uint32_t rank, nranks;
     uint32_t n_local_tiles;
     uint32_t n_chunks;            /* n_local_tiles * 8 warp chunks */
+    /* division by tiles_x / n_chunks as multiply-high (two divisions per 32-pixel chunk were 3 %
+     * of the frame kernel's instructions): q = (v * magic) >> 40, exact while v * d < 2^40;
+     * 0 = the operands of this launch could exceed that, divide */
+    unsigned long long tiles_x_magic, n_chunks_magic;
     uint32_t flags;
     /* compute_pass.comp:50-54 */
     float inv_dim_x, inv_dim_y;

@@ -987,6 +987,17 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.rank = ctx->rank, p.nranks = ctx->nranks;
     p.n_local_tiles = ctx->n_local_tiles;
     p.n_chunks = ctx->n_local_tiles * 8u;
+    {
+        /* multiply-high division (device_scene.h): v * d must stay below 2^40 */
+        const unsigned long long lim = 1ull << 40;
+        const unsigned long long g_max = (unsigned long long)ctx->n_local_padded * ctx->nranks + ctx->nranks;
+        const unsigned long long vc_max = (unsigned long long)p.n_chunks * std::max(n_batch, 1u);
+        /* ... and the 64-bit product v * magic must not overflow: quotient below 2^23 */
+        p.tiles_x_magic = (ctx->tiles_x && g_max * ctx->tiles_x < lim && g_max / ctx->tiles_x < (1ull << 23))
+                              ? lim / ctx->tiles_x + 1ull : 0ull;
+        p.n_chunks_magic = (p.n_chunks && vc_max * p.n_chunks < lim && vc_max / p.n_chunks < (1ull << 23))
+                               ? lim / p.n_chunks + 1ull : 0ull;
+    }
     p.flags = ctx->flags;
     p.inv_dim_x = 1.0f / (float)ctx->W;
     p.inv_dim_y = 1.0f / (float)ctx->H;

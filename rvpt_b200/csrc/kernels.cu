@@ -460,12 +460,18 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
 
 /* ---- slot <-> pixel ------------------------------------------------------- */
 
+/* v / d with the precomputed magic = floor(2^40 / d) + 1 (engine.cu guarantees v * d < 2^40) */
+__device__ __forceinline__ uint32_t div_magic(uint32_t v, uint32_t d, unsigned long long magic)
+{
+    return magic ? (uint32_t)(((unsigned long long)v * magic) >> 40) : v / d;
+}
+
 __device__ __forceinline__ void slot_to_xy(const FrameParams& p, uint32_t slot, uint32_t& x,
                                            uint32_t& y)
 {
     const uint32_t local_tile = slot >> 8;
     const uint32_t g = local_tile * p.nranks + p.rank;
-    const uint32_t ty = g / p.tiles_x;
+    const uint32_t ty = div_magic(g, p.tiles_x, p.tiles_x_magic);
     const uint32_t tx = g - ty * p.tiles_x;
     const uint32_t w = (slot >> 5) & 7u, lane = slot & 31u;
     x = tx * RVPT_TILE_DIM + ((w & 1u) << 3) + (lane & 7u);
@@ -971,7 +977,7 @@ __device__ __forceinline__ void primary_phase(const FrameParams& p, const SceneV
 
       for (uint32_t vc = unit * kChunkGrain, vc_end = min(vc + kChunkGrain, n_vchunks); vc < vc_end; ++vc)
       {
-        const uint32_t fi = kBatch ? vc / p.n_chunks : 0u;
+        const uint32_t fi = kBatch ? div_magic(vc, p.n_chunks, p.n_chunks_magic) : 0u;
         const uint32_t c = kBatch ? vc - fi * p.n_chunks : vc;
         const uint32_t slot = c * 32u + lane;
         const uint32_t tag = kBatch ? (slot | (fi << RVPT_BATCH_SLOT_BITS)) : slot;

@@ -11,10 +11,11 @@ import torch  # noqa: E402
 
 import rvpt_b200 as rv  # noqa: E402
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-W, H, FRAMES = 1920, 1080, 48
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+W, H, FRAMES = 1920, 1080, 64
 out = [f"# Bounce-depth sweep (BASELINE config 5), {W}x{H}, aa 1, {FRAMES} progressive frames per point, 1 x B200\n",
-       "Device-resident throughput (CUDA events around the frame launches, after 8 warm-up frames). "
+       "Device-resident throughput (CUDA events around one rvpt_b200_render_frames call = one batched launch, after a "
+       "warm-up call of the same size). "
        "Warp-divergence counters of the 8-bounce point are in the k_frame ncu capture of the same tag "
        "(`smsp__thread_inst_executed_per_inst_executed.ratio`, `smsp__sass_average_branch_targets_threads_uniform.pct`).\n"]
 for name, scene, pose, fov in (("built-in scene, default pose", rv.builtin_scene(), (0.0, 0.0, 0.0), 90.0),
@@ -27,9 +28,9 @@ for name, scene, pose, fov in (("built-in scene, default pose", rv.builtin_scene
     torch.cuda.set_stream(st)
     eng.set_stream(st.cuda_stream)
     eng.upload_scene(tris, scene.materials, nodes)
-    out.append(f"\n## {name} ({len(tris)} triangles)\n\n| max_bounces | Msamples/s | Mrays/s | us/frame | rays/sample | active rays per bounce (last frame) |\n|---|---|---|---|---|---|\n")
+    out.append(f"\n## {name} ({len(tris)} triangles)\n\n| max_bounces | Msamples/s | Mrays/s | us/frame | rays/sample | active rays per bounce (whole launch) |\n|---|---|---|---|---|---|\n")
     for b in list(range(1, 9)) + [12, 16]:
-        eng.render_frames(rv.default_settings(max_bounces=b, frame=0), cam, 8)
+        eng.render_frames(rv.default_settings(max_bounces=b, frame=0), cam, FRAMES)  # warm-up, same batch size (buffers grow once)
         torch.cuda.synchronize()
         a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st)
