@@ -19,7 +19,8 @@ The workload's bytes (BVH, triangles, materials, camera) are committed under ora
           inside the timed region, wall clock.
   parity_ok  the rgba8 image the last timed step left behind == the CPU oracle's image of the
           same 64 frames, byte for byte (at every N: the image rank 0 assembled).
-  c4      secondary record: BASELINE.json configs[3], 3840x2160 x 16 progressive frames, same
+  c4, c3  secondary records: BASELINE.json configs[3] (3840x2160 x 16 progressive frames) and
+          configs[2] (Cornell box + mesh, mirror / dielectric blocks, 1920x1080 x 16 frames), same
           timing discipline and the same parity check.
 
 N > 1 (one process per GPU): the frame is sharded by 16x16 pixel tile (tile_id % N == rank);
@@ -84,7 +85,8 @@ def parse_args():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the last step")
-    ap.add_argument("--no-c4", action="store_true", help="skip the secondary 3840x2160 x16 record")
+    ap.add_argument("--no-c4", action="store_true",
+                    help="skip the secondary records (C4: 3840x2160 x16; C3: Cornell box 1080p x16)")
     ap.add_argument("--frame-by-frame", action="store_true",
                     help="one rvpt_b200_render_frame call (= one launch) per frame instead of one "
                          "rvpt_b200_render_frames batch per step")
@@ -511,23 +513,35 @@ def run_ours(args):
                "sample": f"{n_frames} full frames of the workload (the oracle run of the parity check), "
                          f"{secs:.1f} s on {cores} threads"}
 
-    # ---- secondary record: C4, 3840x2160 x 16 progressive frames --------------------------------
-    c4 = None
+    # ---- secondary records: C4 (3840x2160 x 16 frames) and C3 (Cornell box, 1080p x 16 frames) ----
+    c4 = c3 = None
     if not args.no_c4 and args.scene == "builtin" and (W, H) == (1920, 1080):
+        run.barrier()
         run.eng.close()
+
+        def secondary(sargs, swl, sw, sh, sframes):
+            r = Runner(sargs, torch, dist, rv, swl, sw, sh, sframes, rank, world, local_rank, stream)
+            ssteps = max(5, args.steps // 2)
+            ms, _ = r.time_steps(ssteps, args.warmup, stream, flush, "off")
+            ok = None if args.no_parity else r.parity()
+            st2 = r.eng.stats()
+            rec = None
+            if rank == 0:
+                rec = {"workload": describe(sargs, len(swl[1]), len(swl[0]), sw, sh, sframes),
+                       "value": ssteps * sw * sh * sframes * args.aa / (ms * 1e-3) / 1e6, "unit": UNIT,
+                       "ms_per_step": ms / ssteps, "steps": ssteps, "frames_per_step": sframes,
+                       "launches_per_step": st2["kernel_launches"], "parity_ok": ok}
+            r.barrier()
+            r.eng.close()
+            return rec
+
         c4_args = argparse.Namespace(**vars(args))
         c4_args.width, c4_args.height, c4_args.frames = 3840, 2160, 16
-        r4 = Runner(c4_args, torch, dist, rv, wl, 3840, 2160, 16, rank, world, local_rank, stream)
-        ms4, _ = r4.time_steps(max(5, args.steps // 2), args.warmup, stream, flush, "off")
-        steps4 = max(5, args.steps // 2)
-        ok4 = None if args.no_parity else r4.parity()
-        st4 = r4.eng.stats()
-        if rank == 0:
-            c4 = {"workload": describe(c4_args, len(tris), len(nodes), 3840, 2160, 16),
-                  "value": steps4 * 3840 * 2160 * 16 * args.aa / (ms4 * 1e-3) / 1e6, "unit": UNIT,
-                  "ms_per_step": ms4 / steps4, "steps": steps4, "frames_per_step": 16,
-                  "launches_per_step": st4["kernel_launches"], "parity_ok": ok4}
-        r4.eng.close()
+        c4 = secondary(c4_args, wl, 3840, 2160, 16)
+        c3_args = argparse.Namespace(**vars(args))
+        c3_args.scene, c3_args.frames = "cornell", 16
+        c3_wl = product_workload(c3_args)
+        c3 = secondary(c3_args, c3_wl, 1920, 1080, 16)
 
     if rank == 0:
         line = {
@@ -558,7 +572,7 @@ def run_ours(args):
                 "what": f"rgba8 image after the last timed step vs the CPU oracle's frames 0..{F - 1}",
                 "differing_pixels": getattr(run, "diff_pixels", None),
                 "image_sha256": getattr(run, "image_sha256", None)},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "c4": c4,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "c4": c4, "c3": c3,
             "mrays_per_s": value * (R / max(S, 1)),
         }
         print(json.dumps(line))

@@ -15,7 +15,7 @@ try:
     lines = [l for l in open("gpurun_out/bench_%s_n%s.json" % (sys.argv[1], sys.argv[2])) if l.startswith("{")]
     d = json.loads(lines[-1])
     print("N", sys.argv[2], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "parity", d["parity_ok"], "ms/step", round(d["ms_per_step"], 3),
-          "c4", d["c4"] and (round(d["c4"]["value"]), d["c4"]["parity_ok"], round(d["c4"]["ms_per_step"], 3)), "launches", d["gpu_launches"], d["run"]["launch"][:60])
+          "c4", d["c4"] and (round(d["c4"]["value"]), d["c4"]["parity_ok"]), "c3", d.get("c3") and (round(d["c3"]["value"]), d["c3"]["parity_ok"]), "launches", d["gpu_launches"], d["run"]["launch"][:60])
 except Exception as e:
     print("N", sys.argv[2], "failed", e)
 PY
