@@ -23,6 +23,7 @@ FLAG_NO_FORECAST = 0x40
 FLAG_REFERENCE_ORDER = 0x80
 FLAG_NO_QUEUE_SORT = 0x100
 FLAG_NO_BATCH = 0x200
+FLAG_GPU_BVH = 0x400
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -93,6 +94,8 @@ SIGNATURES = {
     "rvpt_b200_attach_output2": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvpt_b200_build_bvh": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
                                       C.c_void_p]),
+    "rvpt_b200_build_bvh_gpu": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
+                                          C.c_void_p, C.POINTER(C.c_float)]),
     "rvpt_b200_camera_data": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                      C.c_void_p]),
     "rvpt_b200_has_coincident_faces": (C.c_int, [C.c_void_p, C.c_size_t]),

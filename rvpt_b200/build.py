@@ -21,7 +21,7 @@ ROOT = HERE.parent
 CSRC = HERE / "csrc"
 LIB = HERE / "librvpt_b200.so"
 
-CUDA_SOURCES = ["kernels.cu", "engine.cu"]
+CUDA_SOURCES = ["kernels.cu", "engine.cu", "bvh_gpu.cu"]
 HOST_SOURCES = ["bvh_build.cpp", "camera.cpp"]
 HEADLESS = HERE / "rvpt_headless"
 HEADLESS_SOURCES = [CSRC / "host" / "rvpt_host.cpp", CSRC / "host" / "rvpt_headless.cpp"]

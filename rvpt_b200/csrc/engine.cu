@@ -797,7 +797,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
                   RVPT_B200_FLAG_NO_BATCH | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
-                  RVPT_B200_FLAG_NO_QUEUE_SORT))
+                  RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_GPU_BVH))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
@@ -935,7 +935,10 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
         std::vector<rvpt_bvh_node> built(2 * n_triangles);
         std::vector<uint32_t> perm(n_triangles);
         size_t n_built = 0;
-        rc = rvpt_b200_build_bvh(triangles, n_triangles, built.data(), &n_built, perm.data());
+        if (ctx->flags & RVPT_B200_FLAG_GPU_BVH)
+            rc = rvpt_b200_build_bvh_gpu(ctx->device, triangles, n_triangles, built.data(), &n_built, perm.data(), nullptr);
+        else
+            rc = rvpt_b200_build_bvh(triangles, n_triangles, built.data(), &n_built, perm.data());
         if (rc) return fail(ctx, rc, "internal BVH build failed");
         std::vector<rvpt_triangle> sorted(n_triangles);
         for (size_t i = 0; i < n_triangles; ++i) sorted[i] = triangles[perm[i]];

@@ -54,6 +54,9 @@ constexpr int kWarpsPerCta = kThreads / 32;
 #define RVPT_CHUNK_GRAIN 1
 #endif
 constexpr uint32_t kChunkGrain = RVPT_CHUNK_GRAIN; /* 32-pixel chunks per claim */
+#ifndef RVPT_GLOBAL_CTAS
+#define RVPT_GLOBAL_CTAS 1 /* resident CTAs per SM of the global-memory-path instantiations */
+#endif
 
 #define RV_INF __int_as_float(0x7f800000)
 
@@ -1374,7 +1377,7 @@ __device__ __forceinline__ void resolve_phase(const FrameParams& p, const float*
  * parked, and one resolve phase folds them per pixel in frame order. The scene is staged once
  * and the launch pays max_bounces grid barriers + one for the resolve, not that many per frame. */
 template <bool kSmem, bool kRel, bool kOct, bool kBatch>
-__global__ void __launch_bounds__(kThreads, RVPT_MIN_CTAS) k_frame(const FrameParams p)
+__global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL_CTAS)) k_frame(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;

@@ -39,6 +39,23 @@ def build_bvh(triangles: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     return nodes[: n_nodes.value].copy(), perm
 
 
+def build_bvh_gpu(triangles: np.ndarray, device: int = 0) -> tuple[np.ndarray, np.ndarray, float]:
+    """The same contract built on the GPU (linear BVH, rvpt_b200/csrc/bvh_gpu.cu). Returns
+    (nodes, primitive_indices, device milliseconds of the build kernels)."""
+    lib = _lib.load()
+    tris = np.ascontiguousarray(triangles, TRIANGLE_DTYPE)
+    n = len(tris)
+    nodes = np.zeros(max(2 * n, 1), BVH_NODE_DTYPE)
+    perm = np.zeros(n, np.uint32)
+    n_nodes = C.c_size_t(0)
+    ms = C.c_float(0.0)
+    rc = lib.rvpt_b200_build_bvh_gpu(device, tris.ctypes.data, n, nodes.ctypes.data, C.byref(n_nodes),
+                                     perm.ctypes.data, C.byref(ms))
+    if rc:
+        raise EngineError(rc, "build_bvh_gpu failed")
+    return nodes[: n_nodes.value].copy(), perm, float(ms.value)
+
+
 def camera_data(translation=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0), aspect: float = 2.0,
                 fov: float = 90.0, scale: float = 4.0) -> np.ndarray:
     """Camera::get_data() (camera.cpp:55-66): 20 floats. Defaults are the
