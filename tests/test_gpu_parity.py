@@ -915,3 +915,73 @@ def test_gpu_bvh_builder(rv, oracle_mod, scene_name):
         eng2.render_frame(rv.default_settings(frame=f), cam)
     _assert_bit_equal(eng2.read_accum_f32(), ora.accum, f"GPU BVH built inside upload_scene, {scene_name}")
     print(f"GPU BVH build, {scene_name}: {n} triangles in {ms:.2f} ms (device)")
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_randomised_configurations(rv, oracle_mod, builtin, cornell, seed):
+    """Seeded random walks through the configuration space — image size (ragged), scene, pose,
+    camera, bounce limit, aa, accumulation mode, dispatch rule, implementation flags, tile
+    partition, and a mix of render_frame / render_frames calls of random lengths on ONE engine —
+    each compared with the oracle fed the same frame sequence."""
+    from rvpt_b200 import _lib
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.integers(1, 200)), int(rng.integers(1, 120))
+    prep, pose, fov = (builtin, [DEFAULT_POSE, PINNED_POSE][int(rng.integers(2))], 90.0) if rng.random() < 0.5 \
+        else (cornell, CORNELL_POSE, 60.0)
+    kw = dict(max_bounces=int(rng.choice([1, 2, 3, 8, 8, 8, 16])), aa=int(rng.choice([1, 1, 1, 2, 3])),
+              camera_mode=int(rng.choice([0, 0, 0, 1, 2])))
+    split = None  # now and then another integrator everywhere, or the 4-way split view
+    if rng.random() < 0.15:
+        kw["mode"] = int(rng.integers(0, 9))
+    elif rng.random() < 0.15:
+        split = ([int(v) for v in rng.choice([9, 9, 0, 1, 3, 4, 5, 6, 7, 8], 4)], (float(rng.random()), float(rng.random())))
+
+    def settings(f):
+        rs = rv.default_settings(frame=f, **kw)
+        if split:
+            (rs["top_left_render_mode"], rs["top_right_render_mode"], rs["bottom_left_render_mode"],
+             rs["bottom_right_render_mode"]) = split[0]
+            rs["split_ratio"] = split[1]
+        return rs
+    accum_flags = int(rng.choice([0, 0, _lib.FLAG_ACCUM_RGBA8])) | int(rng.choice([0, 0, _lib.FLAG_REFERENCE_DISPATCH]))
+    impl_flags = 0
+    for f in (_lib.FLAG_NO_OCTANTS, _lib.FLAG_NO_FORECAST, _lib.FLAG_REFERENCE_ORDER, _lib.FLAG_NO_QUEUE_SORT,
+              _lib.FLAG_NO_BATCH, _lib.FLAG_UNFUSED):
+        if rng.random() < 0.2:
+            impl_flags |= f
+    nranks = int(rng.choice([1, 1, 2, 3]))
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes, flags=accum_flags)
+    engines = []
+    for r in range(nranks):
+        e = rv.Engine(W, H, flags=accum_flags | impl_flags, rank=r, nranks=nranks)
+        e.upload_scene(prep.triangles, prep.materials, prep.nodes)
+        engines.append(e)
+    frame = 0
+    for _ in range(int(rng.integers(1, 5))):
+        n = int(rng.choice([1, 1, 2, 5, 9]))
+        batched = rng.random() < 0.6
+        for e in engines:
+            if batched:
+                e.render_frames(settings(frame), cam, n)
+            else:
+                for f in range(frame, frame + n):
+                    e.render_frame(settings(f), cam)
+        for f in range(frame, frame + n):
+            ora.render_frame(settings(f), cam)
+        frame += n
+    what = f"seed {seed}: {W}x{H} {kw} split {split} accum {accum_flags:#x} impl {impl_flags:#x} ranks {nranks}"
+    accs = [e.read_accum_f32() for e in engines]
+    acc = accs[0].copy()
+    for a in accs[1:]:                                   # disjoint supports (NaNs of the depth view stay put)
+        acc = np.where(a.view(np.uint32) != 0, a, acc)
+    rgba = sum(e.read_output_rgba8().astype(np.uint16) for e in engines).astype(np.uint8)
+    if accum_flags & _lib.FLAG_ACCUM_RGBA8:
+        assert np.array_equal(acc, ora.accum_f32()), what
+    else:
+        want = ora.accum
+        same = (acc.view(np.uint32) == want.view(np.uint32)) | (np.isnan(acc) & np.isnan(want))
+        assert same.all(), f"{what}: {(~same).sum()} words differ"
+    assert np.array_equal(rgba, ora.result), what
+    for e in engines:
+        e.close()
