@@ -202,20 +202,42 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_frames(W, H, nodes, tris, mats, cam, frames, bounces, aa, nthreads=0):
-    """Renders frames 0..frames-1 with the CPU oracle. Returns (rgba8 image, seconds, cores)."""
+def cpu_renderer(W, H, nodes, tris, mats):
+    """The CPU implementation of the path that serves as checker and baseline. kind "reference":
+    the reference's own shipped shader binary translated to C++ and compiled for the host
+    (oracle/_ref/libref_shader.so, built next to the reference tree by `make -C oracle ref_shader`;
+    the prebuilt library travels to the GPU box). kind "port": the restatement of the GLSL,
+    oracle/rvpt_oracle.cpp, when that library does not exist. Returns (renderer, kind, cores)."""
     import oracle
-    ora = oracle.OracleRenderer(W, H, tris, mats, nodes, nthreads=nthreads)
-    cores = nthreads or oracle.load().rvpt_oracle_hardware_threads()
+    try:
+        from oracle import ref_shader
+        if ref_shader.LIB_PATH.exists() or ref_shader.REFERENCE_SPV.exists():
+            r = ref_shader.RefShaderRenderer(W, H, tris, mats, nodes)
+            return r, "reference", r.threads()
+    except Exception as exc:  # noqa: BLE001
+        print(f"bench: reference shader library unavailable ({exc}); using the oracle port", file=sys.stderr)
+    ora = oracle.OracleRenderer(W, H, tris, mats, nodes)
+    return ora, "port", oracle.load().rvpt_oracle_hardware_threads()
+
+
+def cpu_image(r, kind):
+    return r.result_rgba8() if kind == "reference" else r.result
+
+
+def oracle_frames(W, H, nodes, tris, mats, cam, frames, bounces, aa):
+    """Renders frames 0..frames-1 on the host CPU. Returns (rgba8 image, seconds, cores, kind)."""
+    import oracle
+    r, kind, cores = cpu_renderer(W, H, nodes, tris, mats)
     t = time.perf_counter()
     for f in range(frames):
-        ora.render_frame(oracle.settings(max_bounces=bounces, aa=aa, frame=f), cam)
-    return ora.result, time.perf_counter() - t, cores
+        r.render_frame(oracle.settings(max_bounces=bounces, aa=aa, frame=f), cam)
+    return cpu_image(r, kind), time.perf_counter() - t, cores, kind
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference shader on the box's host cores (kind
-    "port": the Vulkan path cannot be built here). Loads oracle/ only."""
+    """Reference arm: the reference's own implementation of the path on the box's host cores — its
+    shipped shader binary compiled for the CPU (kind "reference") or, without that library, the
+    restatement of the GLSL (kind "port"). The Vulkan path itself cannot run here. Loads oracle/ only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import oracle
@@ -224,8 +246,7 @@ def run_reference(args):
         wl = product_workload(args)
     nodes, tris, mats, cam = wl
     W, H = args.width, args.height
-    cores = oracle.load().rvpt_oracle_hardware_threads()
-    ora = oracle.OracleRenderer(W, H, tris, mats, nodes)
+    ora, kind, cores = cpu_renderer(W, H, nodes, tris, mats)
     frame = 0
 
     def step():  # one full frame of the workload (a bounded sample of the 64-frame step)
@@ -249,7 +270,10 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": describe(args, len(tris), len(nodes), W, H, args.frames),
                    "frames_per_step": args.frames},
-        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "what": {"reference": "the reference's shipped compute_pass.comp.spv translated to C++ and "
+                                               "compiled for the host (oracle/_ref/libref_shader.so)",
+                                  "port": "CPU restatement of the GLSL (oracle/rvpt_oracle.cpp)"}[kind]},
         "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -375,10 +399,10 @@ class Runner:
         img = self.read_image()
         ok = None
         if self.rank == 0:
-            want, secs, cores = oracle_frames(self.W, self.H, self.nodes, self.tris, self.mats, self.cam,
-                                              self.F, self.args.bounces, self.args.aa)
+            want, secs, cores, kind = oracle_frames(self.W, self.H, self.nodes, self.tris, self.mats, self.cam,
+                                                    self.F, self.args.bounces, self.args.aa)
             ok = bool(np.array_equal(img, want))
-            self.oracle_run = (secs, cores)
+            self.oracle_run = (secs, cores, kind)
             self.image_sha256 = hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
             self.diff_pixels = int((img != want).any(axis=-1).sum())
         if self.world > 1:
@@ -505,13 +529,24 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if getattr(run, "oracle_run", None) is None:
-            _, secs, cores = oracle_frames(W, H, nodes, tris, mats, cam, min(F, 16), args.bounces, args.aa)
+            _, secs, cores, kind = oracle_frames(W, H, nodes, tris, mats, cam, min(F, 16), args.bounces, args.aa)
             n_frames = min(F, 16)
         else:
-            (secs, cores), n_frames = run.oracle_run, F
-        cpu = {"value": n_frames * W * H * args.aa / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_frames} full frames of the workload (the oracle run of the parity check), "
-                         f"{secs:.1f} s on {cores} threads"}
+            (secs, cores, kind), n_frames = run.oracle_run, F
+        cpu = {"value": n_frames * W * H * args.aa / secs / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n_frames} full frames of the workload (the CPU run of the parity check), "
+                         f"{secs:.1f} s on {cores} threads",
+               "what": {"reference": "the reference's shipped compute_pass.comp.spv translated to C++ and compiled "
+                                     "for the host (oracle/_ref/libref_shader.so)",
+                        "port": "CPU restatement of the GLSL (oracle/rvpt_oracle.cpp)"}[kind]}
+        if kind == "reference":
+            # for comparison: the hand-written restatement of the GLSL on the same cores (4 frames)
+            import oracle
+            ora = oracle.OracleRenderer(W, H, tris, mats, nodes)
+            t0p = time.perf_counter()
+            for f in range(4):
+                ora.render_frame(oracle.settings(max_bounces=args.bounces, aa=args.aa, frame=f), cam)
+            cpu["port_value"] = 4 * W * H * args.aa / (time.perf_counter() - t0p) / 1e6
 
     # ---- secondary records: C4 (3840x2160 x 16 frames) and C3 (Cornell box, 1080p x 16 frames) ----
     c4 = c3 = None
@@ -569,7 +604,9 @@ def run_ours(args):
             "gpu_launches": args.steps * launches_per_step,
             "parity_ok": parity_ok,
             "parity": None if args.no_parity else {
-                "what": f"rgba8 image after the last timed step vs the CPU oracle's frames 0..{F - 1}",
+                "what": f"rgba8 image after the last timed step vs frames 0..{F - 1} rendered on the CPU by "
+                        + ("the reference's own compiled shader" if getattr(run, "oracle_run", (0, 0, "port"))[2] == "reference"
+                           else "the oracle"),
                 "differing_pixels": getattr(run, "diff_pixels", None),
                 "image_sha256": getattr(run, "image_sha256", None)},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "c4": c4, "c3": c3,

@@ -12,7 +12,8 @@
  * executes that binary with the reference's bindings; this oracle equals its output bit for bit
  * on every case of tests/golden/make_spirv_golden.py (all configs' shapes, both image formats,
  * every integrator and camera; live in tests/test_spirv_pin.py next to the reference,
- * through committed digests elsewhere). That run found one deviation in round 2 — glslang had
+ * through committed digests elsewhere; oracle/spirv_to_cpp.py additionally compiles the same
+ * binary for the host, oracle/_ref/libref_shader.so). That run found one deviation in round 2 — glslang had
  * folded normalize(vec3(0.5,1,0.3)) in double precision (RV_LIGHT_DIR_* in rvpt_math.h).
  * What stays unpinned is what SPIR-V itself leaves to the Vulkan driver: summation order of
  * dot / mat*vec, accuracy of sin / cos / tan / normalize, UNORM8 rounding (next paragraph).

@@ -985,3 +985,28 @@ def test_randomised_configurations(rv, oracle_mod, builtin, cornell, seed):
     assert np.array_equal(rgba, ora.result), what
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("config", ["C2", "C3"])
+def test_gpu_against_the_reference_shader_compiled_for_the_host(rv, builtin, cornell, config):
+    """The CUDA path against the reference's OWN implementation at full size, live: the shipped
+    compute_pass.comp.spv translated to C++ (oracle/spirv_to_cpp.py) and compiled for the host
+    (oracle/_ref/libref_shader.so — built next to the reference tree, it travels to this box).
+    1920x1080, four progressive frames in one batched launch, every pixel, float32 bit for bit."""
+    from oracle import ref_shader
+    if not ref_shader.LIB_PATH.exists():
+        pytest.skip("oracle/_ref/libref_shader.so was not built (needs the reference tree)")
+    W, H, N = 1920, 1080, 4
+    prep, pose, fov = (builtin, DEFAULT_POSE, 90.0) if config == "C2" else (cornell, CORNELL_POSE, 60.0)
+    cam = rv.camera_data(translation=pose, aspect=W / H, fov=fov)
+    ref = ref_shader.RefShaderRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    for f in range(N):
+        ref.render_frame(rv.default_settings(frame=f), cam)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    for rep in range(2):  # the second launch runs with the forecast / ordered bounce arrays / octant queues on
+        eng.render_frames(rv.default_settings(frame=0), cam, N)
+        got = eng.read_accum_f32()
+        same = got[..., :3].view(np.uint32) == ref.temporal[..., :3].view(np.uint32)
+        assert same.all(), f"{config}, launch {rep}: {(~same).sum()} float32 words differ from the reference's shader"
+        assert np.array_equal(eng.read_output_rgba8()[..., :3], ref.result_rgba8()[..., :3])
