@@ -106,7 +106,7 @@ typedef struct rvpt_b200_stats
     uint32_t kernel_launches;                      /* kernels launched by the last render_frame(s) call */
     uint32_t traversal_order;                      /* 0 reference child order, 1 front to back (see REFERENCE_ORDER) */
     uint32_t frames;                               /* frames the counters cover (1 unless batched) */
-    uint32_t served_waves;                         /* bounce waves of the last launch that used the leaf server */
+    uint32_t reserved;
 } rvpt_b200_stats;
 
 /* ------------------------------------------------------------------------ */
@@ -165,10 +165,6 @@ typedef struct rvpt_b200_stats
 /* rvpt_b200_upload_scene(nodes == NULL) builds its BVH on the GPU (rvpt_b200_build_bvh_gpu)
  * instead of on the host (rvpt_b200_build_bvh). */
 #define RVPT_B200_FLAG_GPU_BVH 0x400u
-/* Closed scenes: every warp tests its own leaves' triangles inside the node loop instead of
- * posting them to the CTA's tester warps (kernels.cu, "leaf server"). Same results; for A/B
- * measurements. */
-#define RVPT_B200_FLAG_NO_LEAF_SERVER 0x800u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 

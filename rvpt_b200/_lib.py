@@ -24,7 +24,6 @@ FLAG_REFERENCE_ORDER = 0x80
 FLAG_NO_QUEUE_SORT = 0x100
 FLAG_NO_BATCH = 0x200
 FLAG_GPU_BVH = 0x400
-FLAG_NO_LEAF_SERVER = 0x800
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -37,7 +36,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint32),
         ("traversal_order", C.c_uint32),
         ("frames", C.c_uint32),
-        ("served_waves", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -149,7 +149,6 @@ struct WaveCounters
 struct FrameStats
 {
     unsigned long long active[64]; /* rays traced at bounce b */
-    unsigned long long served_waves; /* bounce waves whose triangle tests ran on the tester warps */
 };
 struct FrameCounters
 {

@@ -797,11 +797,8 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
                   RVPT_B200_FLAG_NO_BATCH | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
-                  RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_GPU_BVH | RVPT_B200_FLAG_NO_LEAF_SERVER))
+                  RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_GPU_BVH))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
-    if (const char* e = std::getenv("RVPT_B200_AB_FLAGS")) /* developer knob: A/B runs of the scheduling-only flags */
-        flags |= (uint32_t)std::strtoul(e, nullptr, 0) &
-                 (RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_NO_LEAF_SERVER);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
@@ -1296,7 +1293,6 @@ extern "C" int rvpt_b200_get_stats(rvpt_b200_ctx* ctx, rvpt_b200_stats* out)
     out->kernel_launches = ctx->last_launches;
     out->traversal_order = ctx->layout.off_oct != 0u ? 1u : 0u;
     out->frames = ctx->last_frames;
-    out->served_waves = (uint32_t)h.served_waves;
     return 0;
 }
 

@@ -411,288 +411,9 @@ __device__ __noinline__ uint2 retrace_reference_order(uint32_t nodes, uint32_t t
     return make_uint2(__float_as_uint(t), tri);
 }
 
-
-/* ---- leaf server: the triangle tests of a closed scene's bounce waves, gathered ------------ */
-/* In a closed scene the lanes of a warp reach their leaves at different steps of the node loop:
- * the triangle test (65 of the loop's ~95 instructions) ran for TWO lanes of 32 on average and
- * took 44 % of all issue slots of the Cornell box (`profiles/r02_k_frame_hot_blocks_cornell.txt`).
- * Votes inside the node loop to gather those lanes cost more than they save (round 1's
- * while-while walk, round 2's leaf batching). So the walker does not test at all: a lane that
- * enters a leaf posts (ray origin, direction, first triangle, ray id) to a ring in shared memory
- * and walks on; RVPT_SRV_TESTERS warps of the CTA do nothing but drain the rings, 32 posted
- * (ray, leaf) pairs per instruction, and fold every accepted hit into the ray's nearest-hit word
- * (clip distance | triangle) with a compare-and-swap. The walker clips its boxes against that
- * word, read afresh at every node; a stale value only means a node or a leaf too many — the
- * relaxed-walk argument above already covers every order of the tests — and before it shades,
- * the lane waits until the ring's consumer has passed its last post.
- *
- * Memory: the eight origin-relative node copies are dead once the primary wave is over (a grid
- * barrier ago); their first halves hold the nearest-hit words and the rings. */
-#ifndef RVPT_SRV_TESTERS
-#define RVPT_SRV_TESTERS 4u
-#endif
-#ifndef RVPT_SRV_RING
-#define RVPT_SRV_RING 128u /* posts per ring, a power of two */
-#endif
-#ifndef RVPT_SRV_WAIT_NS
-#define RVPT_SRV_WAIT_NS 256 /* a waiting warp must not take issue slots from the testers it waits for */
-#endif
-#define RVPT_SRV_BEST_BYTES (8u * (uint32_t)kThreads)
-#define RVPT_SRV_HEAD 0u
-#define RVPT_SRV_TAIL 4u
-#define RVPT_SRV_READY 16u
-#define RVPT_SRV_POSTS (RVPT_SRV_READY + 4u * RVPT_SRV_RING)
-#define RVPT_SRV_RING_BYTES (RVPT_SRV_POSTS + 32u * RVPT_SRV_RING)
-#define RVPT_SRV_DONE (RVPT_SRV_BEST_BYTES + RVPT_SRV_TESTERS * RVPT_SRV_RING_BYTES)
-#define RVPT_SRV_BYTES (RVPT_SRV_DONE + 16u)
-constexpr uint32_t kSrvWalkers = (uint32_t)kWarpsPerCta - RVPT_SRV_TESTERS;
-
-__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a)
-{
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_acquire_u32(uint32_t a)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_release_u32(uint32_t a, uint32_t v)
-{
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v)
-{
-    uint32_t r;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
-    return r;
-}
-__device__ __forceinline__ void reds_add_release_u32(uint32_t a, uint32_t v)
-{
-    asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long atoms_cas_u64(uint32_t a, unsigned long long cmp,
-                                                            unsigned long long val)
-{
-    unsigned long long r;
-    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(r) : "r"(a), "l"(cmp), "l"(val) : "memory");
-    return r;
-}
-
-/* what a walker thread knows of the server (registers) */
-struct LeafServer
-{
-    uint32_t ring;   /* shared address of the ring this warp posts to */
-    uint32_t best;   /* shared address of this thread's nearest-hit word: {triangle, clip distance} */
-    uint32_t ticket; /* 1 + position of this ray's last post; 0 = it posted nothing */
-    uint32_t mask;   /* lanes of the warp that trace a ray in this round */
-};
-
-__device__ __forceinline__ LeafServer srv_handle(uint32_t base)
-{
-    LeafServer s;
-    s.best = base + 8u * threadIdx.x;
-    s.ring = base + RVPT_SRV_BEST_BYTES + ((threadIdx.x >> 5) % RVPT_SRV_TESTERS) * RVPT_SRV_RING_BYTES;
-    s.ticket = 0u;
-    s.mask = 0xFFFFFFFFu;
-    /* opaque to ptxas, which otherwise re-derives both addresses inside the node loop */
-    asm volatile("" : "+r"(s.best), "+r"(s.ring));
-    return s;
-}
-
-/* block-wide, before the wave's first post */
-__device__ __forceinline__ void srv_reset(uint32_t base)
-{
-    for (uint32_t i = threadIdx.x; i < (RVPT_SRV_BYTES - RVPT_SRV_BEST_BYTES) / 4u; i += blockDim.x)
-    {
-        const uint32_t off = RVPT_SRV_BEST_BYTES + 4u * i;
-        const uint32_t in_ring = (off - RVPT_SRV_BEST_BYTES) % RVPT_SRV_RING_BYTES;
-        if (off >= RVPT_SRV_DONE || in_ring < RVPT_SRV_POSTS)
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + off), "r"(0u) : "memory");
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void srv_begin(LeafServer& s)
-{
-    /* the previous ray of this thread waited for its last post: nobody else touches the word */
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s.best), "r"(0xFFFFFFFFu), "r"(0x7f800000u) : "memory");
-    s.ticket = 0u;
-}
-
-__device__ __forceinline__ void srv_post(LeafServer& s, rv_f3 o, rv_f3 d, uint32_t leaf)
-{
-    const uint32_t pos = atoms_add_u32(s.ring + RVPT_SRV_TAIL, 1u);
-    /* the slot is free once the consumer has passed the post that used it last; the stores below
-     * depend on this load through the branch */
-    for (uint32_t spins = 0; pos - lds_volatile_u32(s.ring + RVPT_SRV_HEAD) >= RVPT_SRV_RING; __nanosleep(RVPT_SRV_WAIT_NS))
-        if (++spins > (1u << 24)) __trap(); /* a stuck ring must fail the launch, not hang the GPU */
-    const uint32_t k = pos & (RVPT_SRV_RING - 1u);
-    const uint32_t e = s.ring + RVPT_SRV_POSTS + 32u * k;
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(e), "f"(o.x), "f"(o.y), "f"(o.z),
-                 "f"(__uint_as_float(s.best))
-                 : "memory");
-    asm volatile("st.shared.v4.f32 [%0+16], {%1, %2, %3, %4};" ::"r"(e), "f"(d.x), "f"(d.y), "f"(d.z),
-                 "f"(__uint_as_float(leaf))
-                 : "memory");
-    sts_release_u32(s.ring + RVPT_SRV_READY + 4u * k, pos + 1u);
-    s.ticket = pos + 1u;
-}
-
-/* The walk is over. Every lane of s.mask calls (the lanes of a warp post to one ring, in order:
- * the warp's last post is its highest ticket): the warp reconverges — the lanes leave the node
- * loop one by one, and whoever waited alone would shade alone —, waits until the ring's consumer
- * has passed that post, and fetches the results (clip distance, flagged triangle). */
-__device__ __forceinline__ void srv_end(const LeafServer& s, bool walked, float& best_t, uint32_t& best_tri)
-{
-    __syncwarp(s.mask);
-    const uint32_t last = __reduce_max_sync(s.mask, walked ? s.ticket : 0u);
-    if (last)
-        for (uint32_t spins = 0; (int32_t)(lds_acquire_u32(s.ring + RVPT_SRV_HEAD) - last) < 0; __nanosleep(RVPT_SRV_WAIT_NS))
-            if (++spins > (1u << 24)) __trap();
-    if (walked)
-    {
-        uint32_t tri, clip;
-        asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tri), "=r"(clip) : "r"(s.best) : "memory");
-        best_t = __uint_as_float(clip);
-        best_tri = tri;
-    }
-}
-
-/* the walker's node loop: walk_nearest<true, false, true> with the leaf test replaced by a post */
-__device__ __forceinline__ void walk_served(uint32_t nodes, rv_f3 o, rv_f3 d, float ix, float iy, float iz,
-                                            LeafServer& s)
-{
-    uint32_t node = 0;
-    while (node != RVPT_NODE_END)
-    {
-        const uint32_t a = nodes + node * 16u;
-        const float4 n0 = lds_f4_off<0>(a);
-        const float4 n1 = lds_f4_off<RVPT_OCT_B_OFFSET>(a);
-        const float clip = __uint_as_float(lds_volatile_u32(s.best + 4u));
-        const float fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
-        const float fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
-        const float fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
-        const float t0 = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
-        const float t1 = fminf(fminf(fx, fy), fminf(fz, clip));
-        const uint32_t skip = __float_as_uint(n1.z);
-        const uint32_t leaf = __float_as_uint(n1.w);
-        if (t1 >= t0)
-        {
-            if (!(leaf & RVPT_NODE_INNER))
-            {
-                srv_post(s, o, d, leaf);
-                node = skip;
-            }
-            else
-                node = node + 1;
-        }
-        else
-            node = skip;
-    }
-}
-
-/* A tester warp: drains one ring until every walker warp of the CTA has reported the end of
- * its wave (a walker reports after its lanes have waited for their posts, so nothing is
- * pending then). test_leaf<true, false, relaxed>'s arithmetic; the update is the same function
- * of (nearest so far, this hit), applied with compare-and-swap because two posts of one batch
- * may belong to the same ray. */
-__device__ __forceinline__ void srv_tester(const SceneViewT<true>& sc, uint32_t base)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ring = base + RVPT_SRV_BEST_BYTES +
-                          ((threadIdx.x >> 5) - kSrvWalkers) * RVPT_SRV_RING_BYTES;
-    uint32_t head = 0, idle = 0;
-    for (;;)
-    {
-        const uint32_t pos = head + lane;
-        const uint32_t k = pos & (RVPT_SRV_RING - 1u);
-        const bool ready = lds_acquire_u32(ring + RVPT_SRV_READY + 4u * k) == pos + 1u;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
-        /* posts are consumed in order: the leading ones that are ready */
-        const uint32_t n = m == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
-        if (n == 0u)
-        {
-            if (lds_acquire_u32(base + RVPT_SRV_DONE) == kSrvWalkers) break;
-            if (++idle > (1u << 26)) __trap();
-            __nanosleep(100);
-            continue;
-        }
-        idle = 0;
-        if (lane < n)
-        {
-            const uint32_t e = ring + RVPT_SRV_POSTS + 32u * k;
-            const float4 P = lds_f4_off<0>(e), Q = lds_f4_off<16>(e);
-            const rv_f3 o = rv_make(P.x, P.y, P.z), d = rv_make(Q.x, Q.y, Q.z);
-            const uint32_t word = __float_as_uint(P.w);
-            uint32_t i = __float_as_uint(Q.w), meta;
-            do
-            {
-                const float4 A = ld_f4<true>(sc.tris, 4 * i + 0);
-                const float4 B = ld_f4<true>(sc.tris, 4 * i + 1);
-                meta = ld_u32<true>(sc.meta, i);
-                const float num = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z), rv_make(B.x, B.y, B.z));
-                const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
-                const float t = num / den;
-                if (0.0f < t && t < __uint_as_float(lds_volatile_u32(word + 4u)))
-                {
-                    const float4 C = ld_f4<true>(sc.tris, 4 * i + 2);
-                    const float4 D = ld_f4<true>(sc.tris, 4 * i + 3);
-                    const float tx = t * d.x, ty = t * d.y, tz = t * d.z;
-                    const rv_f3 p0 = rv_make((o.x + tx) - A.x, (o.y + ty) - A.y, (o.z + tz) - A.z);
-                    const float bx = rv_dot(p0, rv_make(C.x, C.y, C.z));
-                    const float by = rv_dot(p0, rv_make(D.x, D.y, D.z));
-                    const float m0 = B.w * bx, m1 = C.w * by;
-                    const float m2 = C.w * bx, m3 = D.w * by;
-                    const float u = A.w * (m0 + m1);
-                    const float v = A.w * (m2 + m3);
-                    if (0.0f < u && 0.0f < v && u + v < 1.0f)
-                    {
-                        const float tc = clip_of(t);
-                        uint32_t cur_tri, cur_clip;
-                        asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
-                                     : "=r"(cur_tri), "=r"(cur_clip)
-                                     : "r"(word)
-                                     : "memory");
-                        for (;;)
-                        {
-                            const float best_t = __uint_as_float(cur_clip);
-                            if (!(t < best_t)) break; /* beyond the band of the nearest so far */
-                            uint32_t new_tri, new_clip;
-                            if (tc < best_t)
-                            {
-                                new_tri = (best_t <= clip_of(tc)) ? (i | RVPT_TRI_AMBIGUOUS) : i;
-                                new_clip = __float_as_uint(tc);
-                            }
-                            else
-                            {
-                                new_tri = cur_tri | RVPT_TRI_AMBIGUOUS;
-                                new_clip = cur_clip;
-                            }
-                            const unsigned long long cur = ((unsigned long long)cur_clip << 32) | cur_tri;
-                            const unsigned long long nxt = ((unsigned long long)new_clip << 32) | new_tri;
-                            if (nxt == cur) break;
-                            const unsigned long long got = atoms_cas_u64(word, cur, nxt);
-                            if (got == cur) break;
-                            cur_tri = (uint32_t)got, cur_clip = (uint32_t)(got >> 32);
-                        }
-                    }
-                }
-                ++i;
-            } while (!(meta & RVPT_TRI_LAST));
-        }
-        __syncwarp();
-        head += n;
-        if (lane == 0) sts_release_u32(ring + RVPT_SRV_HEAD, head);
-    }
-}
-
-template <bool kSmem, bool kRel, bool kOct, bool kServed = false>
+template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d,
-                                              float& best_t, uint32_t& best_tri,
-                                              LeafServer* srv = nullptr)
+                                              float& best_t, uint32_t& best_tri)
 {
     /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction */
     const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
@@ -706,8 +427,7 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
          * reference's min/max formulation. */
         const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
         const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-        const bool regular = lo > 0.0f && hi < RV_INF;
-        if (regular)
+        if (lo > 0.0f && hi < RV_INF)
         {
             const uint32_t oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
                                  ((__float_as_uint(iz) >> 31) << 2);
@@ -715,31 +435,26 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
             /* opaque to ptxas, which otherwise re-derives this address (shared window base,
              * constant-bank loads, octant bits) inside the node loop to save a register */
             asm volatile("" : "+r"(base));
-            if constexpr (kServed)
+#ifdef RVPT_PROBE_NO_RELAXED
+            walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+#else
+            walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+            if (best_tri != 0xFFFFFFFFu)
             {
-                srv_begin(*srv);
-                walk_served(base, o, d, ix, iy, iz, *srv);
+                if (hit_is_ambiguous(best_tri))
+                    /* a runner-up within rounding distance of the nearest hit: the reference's own
+                     * walk decides (plain node array, reference child order, exact clipping) */
+                {
+                    const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d);
+                    best_t = __uint_as_float(r.x), best_tri = r.y;
+                }
+                else
+                    best_t = exact_of(best_t);
             }
-            else
-                walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
+#endif
         }
         else
             walk_nearest<kSmem, false, false>(sc, sc.nodes, o, d, ix, iy, iz, best_t, best_tri);
-        if constexpr (kServed) srv_end(*srv, regular, best_t, best_tri); /* warp-wide: outside the branch */
-#ifndef RVPT_PROBE_NO_RELAXED
-        if (regular && best_tri != 0xFFFFFFFFu)
-        {
-            if (hit_is_ambiguous(best_tri))
-                /* a runner-up within rounding distance of the nearest hit: the reference's own
-                 * walk decides (plain node array, reference child order, exact clipping) */
-            {
-                const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d);
-                best_t = __uint_as_float(r.x), best_tri = r.y;
-            }
-            else
-                best_t = exact_of(best_t);
-        }
-#endif
     }
     else
         walk_nearest<kSmem, kRel, false>(sc, kRel ? sc.rel_nodes : sc.nodes, o, d, ix, iy, iz, best_t,
@@ -899,13 +614,12 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
-template <bool kSmem, bool kRel, bool kOct, bool kServed = false>
-__device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample,
-                                            LeafServer* srv = nullptr)
+template <bool kSmem, bool kRel, bool kOct>
+__device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
-    trace_nearest<kSmem, kRel, kOct, kServed>(sc, s.o, s.d, t, tri, srv);
+    trace_nearest<kSmem, kRel, kOct>(sc, s.o, s.d, t, tri);
 
     if (tri == 0xFFFFFFFFu)
     {
@@ -1171,11 +885,10 @@ __device__ __forceinline__ void finish_launch(const FrameParams& p)
         uint32_t* w = reinterpret_cast<uint32_t*>(&p.ctr->wave);
         for (uint32_t i = threadIdx.x; i < sizeof(WaveCounters) / 4; i += blockDim.x) w[i] = 0u;
     }
-    if (p.last_of_frame && threadIdx.x < sizeof(FrameStats) / 8u)
+    if (p.last_of_frame && threadIdx.x < 64u)
     {
-        unsigned long long* now = reinterpret_cast<unsigned long long*>(&p.ctr->stats);
-        reinterpret_cast<unsigned long long*>(&p.ctr->last)[threadIdx.x] = __ldcg(&now[threadIdx.x]);
-        now[threadIdx.x] = 0ull;
+        p.ctr->last.active[threadIdx.x] = __ldcg(&p.ctr->stats.active[threadIdx.x]);
+        p.ctr->stats.active[threadIdx.x] = 0ull;
     }
     if (threadIdx.x == 0)
     {
@@ -1374,24 +1087,10 @@ __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathSt
  */
 #define RVPT_WAVE_SPREAD 1u
 #define RVPT_WAVE_SHARDED 4u /* big wave, every 32-ray group claimed from the sharded counters */
-template <bool kSmem, bool kOct, bool kInThread, bool kBatch = false, bool kServed = false>
+template <bool kSmem, bool kOct, bool kInThread, bool kBatch = false>
 __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneViewT<kSmem>& sc, int b,
                                              const WaveGroups& wg, uint32_t mode, bool sort)
 {
-    /* kServed (sharded waves of closed scenes only: every group is claimed, so the tester warps
-     * are not missed in the deal): the last RVPT_SRV_TESTERS warps of the CTA serve triangle tests */
-    static_assert(!kServed || (kSmem && kOct && !kInThread), "leaf server: shared-memory octant walk, queued waves");
-    LeafServer srv;
-    if constexpr (kServed)
-    {
-        srv_reset((uint32_t)sc.oct_rel_nodes);
-        if ((threadIdx.x >> 5) >= kSrvWalkers)
-        {
-            srv_tester(sc, (uint32_t)sc.oct_rel_nodes);
-            return;
-        }
-        srv = srv_handle((uint32_t)sc.oct_rel_nodes);
-    }
     WaveCounters& wc = p.ctr->wave;
     const PathQueue qin = p.queue[(b - 1) & 1];
     const PathQueue qout = p.queue[b & 1];
@@ -1453,7 +1152,6 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
         bool alive = false;
         PathState s;
         uint32_t slot = 0;
-        if constexpr (kServed) srv.mask = __ballot_sync(0xFFFFFFFFu, lane < L && i < wg.cnt[k]);
         if (lane < L && i < wg.cnt[k])
         {
             load_path(qin, k * p.bin_cap + i, s, slot); /* slot: the path's tag */
@@ -1461,7 +1159,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             rv_f3 sample;
             for (int k = b;; ++k)
             {
-                alive = kajiya_step<kSmem, false, kOct, kServed>(sc, s, sample, &srv);
+                alive = kajiya_step<kSmem, false, kOct>(sc, s, sample);
                 if (alive && k == p.max_bounces - 1)
                 {
                     alive = false; /* integrators.glsl:674-675: col is discarded */
@@ -1473,12 +1171,6 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             if (!alive) finish_sample<kBatch>(p, slot, sample, s.rng);
         }
         if (!in_thread) push_survivors(p, qout, wc.qcount[b], alive, slot, s, sort);
-    }
-    if constexpr (kServed)
-    {
-        /* every lane of this warp has waited for its posts: tell the testers */
-        __syncwarp();
-        if (lane == 0) reds_add_release_u32((uint32_t)sc.oct_rel_nodes + RVPT_SRV_DONE, 1u);
     }
 }
 
@@ -1763,19 +1455,7 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
             stamp(p, 2 * b + 2);
             break;
         }
-        bool served = false;
-        if constexpr (kSmem && kOct)
-        {
-            /* closed scene, big wave, and the dead origin-relative node copies have room for the rings */
-            served = ordered_bounce != 0u && deal == RVPT_WAVE_SHARDED && !(p.flags & RVPT_B200_FLAG_NO_LEAF_SERVER) &&
-                     8u * sc.oct_stride >= RVPT_SRV_BYTES;
-            if (served)
-            {
-                if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.ctr->stats.served_waves, 1ull);
-                bounce_phase<kSmem, kOct, false, kBatch, true>(p, sc, b, wg, deal, sort);
-            }
-        }
-        if (!served) bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
+        bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
         stamp(p, 2 * b + 2);
     }
     if constexpr (kBatch)

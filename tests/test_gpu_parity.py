@@ -645,39 +645,6 @@ def test_octant_sorted_queues_are_scheduling_only(rv, oracle_mod, cornell, unfus
         assert st_a[-1][0]["active"] == st_b[-1][0]["active"] == st_a[-1][1]
 
 
-def test_leaf_server_is_scheduling_only(rv, oracle_mod):
-    """Closed scenes, big bounce waves: the walkers post the leaves they enter to the CTA's tester
-    warps instead of testing the triangles themselves (kernels.cu, "leaf server"). The nearest hit
-    of a ray does not depend on who tests its triangles or when: batched and frame-by-frame
-    launches with the server equal the oracle and the launches without it, the counters say the
-    server ran, and RVPT_B200_FLAG_NO_LEAF_SERVER turns it off. The scene with block bottoms IN
-    the floor plane has exact ties (ambiguous hits, re-traced in the reference's order)."""
-    from rvpt_b200 import _lib
-    from conftest import PreparedScene
-    W, H = 960, 540
-    for gap in (0.02, 0.0):
-        prep = PreparedScene(rv, rv.cornell_scene(block_gap=gap))
-        # the first launch has no forecast yet (open-scene schedule); the server starts with the second
-        on, ora = _batched_vs_oracle(rv, oracle_mod, prep, W, H, CORNELL_POSE, [2, 6, 4], fov=60.0)
-        assert on.stats()["served_waves"] >= 5, on.stats()
-        _assert_bit_equal(on.read_accum_f32(), ora.accum, f"leaf server, batched, gap {gap}")
-        off, _ = _batched_vs_oracle(rv, oracle_mod, prep, W, H, CORNELL_POSE, [2, 6, 4], fov=60.0,
-                                       flags=_lib.FLAG_NO_LEAF_SERVER)
-        assert off.stats()["served_waves"] == 0
-        _assert_bit_equal(off.read_accum_f32(), ora.accum, f"no leaf server, gap {gap}")
-    # frame by frame (classic launches) with the server, UNORM8 accumulation
-    prep = PreparedScene(rv, rv.cornell_scene())
-    cam = rv.camera_data(translation=CORNELL_POSE, aspect=W / H, fov=60.0)
-    eng = rv.Engine(W, H, flags=_lib.FLAG_NO_BATCH | 0x1)
-    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
-    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes, flags=0x1)
-    for f in range(4):
-        eng.render_frame(rv.default_settings(frame=f), cam)
-        ora.render_frame(rv.default_settings(frame=f), cam)
-    assert eng.stats()["served_waves"] >= 5, eng.stats()
-    assert np.array_equal(eng.read_output_rgba8(), ora.result)
-
-
 # ---- batched launches: rvpt_b200_render_frames merges the waves of consecutive frames --------
 
 def _batched_vs_oracle(rv, oracle_mod, prep, W, H, pose, batches, flags=0, fov=90.0, rank=0, nranks=1,
