@@ -987,6 +987,56 @@ def test_randomised_configurations(rv, oracle_mod, builtin, cornell, seed):
         e.close()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_camera_poses(rv, oracle_mod, builtin, cornell, seed):
+    """The front-to-back walk is exact for every view, not just the three poses of the stated
+    configurations: seeded random camera positions (inside, outside and on the walls of the scene's
+    box), orientations (all three angles) and fields of view; 640x360 x 6 frames (1920x1080 x 16
+    for the last four) in two batched launches (the second one runs with the forecast, the ordered
+    bounce arrays and the octant queues), compared with the oracle bit for bit — running mean,
+    result image, ray counts."""
+    rng = np.random.default_rng(7000 + seed)
+    prep = cornell if seed % 2 else builtin
+    v = np.concatenate([prep.triangles[k][:, :3] for k in ("vertex0", "vertex1", "vertex2")])
+    lo, hi = v.min(0), v.max(0)
+    kind = seed % 3
+    big = seed >= 20                                               # four of them at the stated size
+    (W, H), batches = ((1920, 1080), (4, 12)) if big else ((640, 360), (2, 4))
+    for attempt in range(40):                                      # until the view shows the scene
+        pos = lo + (hi - lo) * rng.random(3)                       # inside the bounding box
+        if kind == 1:
+            pos = lo - 0.5 * (hi - lo) + 2.0 * (hi - lo) * rng.random(3)  # anywhere around it
+        elif kind == 2:
+            pos[int(rng.integers(3))] = [lo, hi][int(rng.integers(2))][int(rng.integers(3))]  # on a bounding plane
+        rot = rng.uniform(-180.0, 180.0, 3) * np.array([1.0, 0.5, 0.25])
+        cam = rv.camera_data(translation=pos.astype(np.float32), rotation=rot.astype(np.float32), aspect=W / H,
+                             fov=float(rng.uniform(25.0, 120.0)))
+        probe = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+        probe.render_frame(rv.default_settings(frame=0), cam)
+        if probe.active[1] * 10 > W * H:
+            break
+    else:
+        pytest.fail("no pose found that sees the scene")
+    eng = rv.Engine(W, H)
+    eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    frame = 0
+    for n in batches:
+        eng.render_frames(rv.default_settings(frame=frame), cam, n)
+        want = np.zeros(64, np.uint64)
+        for f in range(frame, frame + n):
+            ora.render_frame(rv.default_settings(frame=f), cam)
+            want += ora.active
+        frame += n
+        got = np.zeros(64, np.uint64)
+        st = eng.stats()
+        got[:len(st["active"])] = st["active"]
+        assert st["frames"] == n and np.array_equal(got, want), f"seed {seed}: ray counts"
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"seed {seed}: pose {pos} rotation {rot}")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    eng.close()
+
+
 @pytest.mark.parametrize("config", ["C2", "C3"])
 def test_gpu_against_the_reference_shader_compiled_for_the_host(rv, builtin, cornell, config):
     """The CUDA path against the reference's OWN implementation at full size, live: the shipped
