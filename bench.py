@@ -241,6 +241,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import oracle
+    from oracle import vulkan_probe
     wl = committed_workload(args)
     if wl is None:  # generated scenes have no committed copy: build them with the host helpers
         wl = product_workload(args)
@@ -273,7 +274,9 @@ def run_reference(args):
         "cpu_baseline": {"value": msps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "what": {"reference": "the reference's shipped compute_pass.comp.spv translated to C++ and "
                                                "compiled for the host (oracle/_ref/libref_shader.so)",
-                                  "port": "CPU restatement of the GLSL (oracle/rvpt_oracle.cpp)"}[kind]},
+                                  "port": "CPU restatement of the GLSL (oracle/rvpt_oracle.cpp)"}[kind],
+                         # could the reference's Vulkan path itself run here (a software ICD)? SURVEY 8 f-4
+                         "vulkan": vulkan_probe.probe()},
         "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
