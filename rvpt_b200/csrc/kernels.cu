@@ -54,14 +54,22 @@ constexpr int kWarpsPerCta = kThreads / 32;
 #define RVPT_CHUNK_GRAIN 1
 #endif
 constexpr uint32_t kChunkGrain = RVPT_CHUNK_GRAIN; /* 32-pixel chunks per claim */
-#ifndef RVPT_REFILL_MODE
-#define RVPT_REFILL_MODE 1 /* lane refill in bounce waves: 0 never, 1 closed scenes, 2 every queued wave */
-#endif
 #ifndef RVPT_GLOBAL_CTAS
 #define RVPT_GLOBAL_CTAS 1 /* resident CTAs per SM of the global-memory-path instantiations */
 #endif
 
 #define RV_INF __int_as_float(0x7f800000)
+
+/* A condition every lane of the warp agrees on, said in a way ptxas can see: a branch on a vote
+ * needs no convergence barrier. It matters because the triangle tests of a bounce wave sit ten
+ * divergent regions deep (wave loop, claim loop, lanes with a ray, node loop, leaf, plane test,
+ * ...) and only the barrier registers B0-B7 survive the slow-path call of an IEEE division
+ * untouched: with the claim loop's two exits on plain compares the plane test's own region got B8
+ * and ptxas saved and restored it (BMOV, a slow instruction) around EVERY plane test. With the
+ * exits on votes the queued bounce waves carry no BMOV: Cornell box +5.3 %, C2 +0.6 %, pinned pose
+ * +1.7 % (profiles/r02_experiments.md; the same trick on the primary wave's claim loop or the wave
+ * loop of k_frame costs C2 1-2 % — a vote per 32-pixel chunk — and stays out). */
+__device__ __forceinline__ bool warp_uniform(bool c) { return __all_sync(0xFFFFFFFFu, c); }
 
 /* ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------- */
 
@@ -414,25 +422,6 @@ __device__ __noinline__ uint2 retrace_reference_order(uint32_t nodes, uint32_t t
     return make_uint2(__float_as_uint(t), tri);
 }
 
-/* After a relaxed walk: (clip distance, possibly flagged triangle) -> the reference's (t, triangle) */
-template <bool kSmem>
-__device__ __forceinline__ void settle_relaxed_hit(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d, float& best_t,
-                                                   uint32_t& best_tri)
-{
-    if (best_tri != 0xFFFFFFFFu)
-    {
-        if (hit_is_ambiguous(best_tri))
-            /* a runner-up within rounding distance of the nearest hit: the reference's own
-             * walk decides (plain node array, reference child order, exact clipping) */
-        {
-            const uint2 r = retrace_reference_order((uint32_t)sc.nodes, (uint32_t)sc.tris, (uint32_t)sc.meta, o, d);
-            best_t = __uint_as_float(r.x), best_tri = r.y;
-        }
-        else
-            best_t = exact_of(best_t);
-    }
-}
-
 template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3 o, rv_f3 d,
                                               float& best_t, uint32_t& best_tri)
@@ -461,7 +450,18 @@ __device__ __forceinline__ void trace_nearest(const SceneViewT<kSmem>& sc, rv_f3
             walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
 #else
             walk_nearest<kSmem, kRel, true>(sc, base, o, d, ix, iy, iz, best_t, best_tri);
-            settle_relaxed_hit(sc, o, d, best_t, best_tri);
+            if (best_tri != 0xFFFFFFFFu)
+            {
+                if (hit_is_ambiguous(best_tri))
+                    /* a runner-up within rounding distance of the nearest hit: the reference's own
+                     * walk decides (plain node array, reference child order, exact clipping) */
+                {
+                    const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, d);
+                    best_t = __uint_as_float(r.x), best_tri = r.y;
+                }
+                else
+                    best_t = exact_of(best_t);
+            }
 #endif
         }
         else
@@ -625,24 +625,13 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
-template <bool kSmem>
-__device__ __forceinline__ bool kajiya_shade(const SceneViewT<kSmem>& sc, PathState& s, float t, uint32_t tri,
-                                             rv_f3& sample);
-
 template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
     trace_nearest<kSmem, kRel, kOct>(sc, s.o, s.d, t, tri);
-    return kajiya_shade<kSmem>(sc, s, t, tri, sample);
-}
 
-/* everything of the iteration after intersect_scene: (t, tri) = the nearest hit, 0xFFFFFFFF = none */
-template <bool kSmem>
-__device__ __forceinline__ bool kajiya_shade(const SceneViewT<kSmem>& sc, PathState& s, float t, uint32_t tri,
-                                             rv_f3& sample)
-{
     if (tri == 0xFFFFFFFFu)
     {
         /* :578-579 background */
@@ -803,7 +792,7 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
  * barrier); wg lives in shared memory and its previous readers are behind the grid barrier /
  * kernel boundary that precedes every wave. Returns the wave's ray count (block-uniform). */
 __device__ __forceinline__ uint32_t prepare_wave(const FrameParams& p, WaveGroups& wg, const uint32_t* qcount,
-                                                 uint32_t spread_below, uint32_t big_group = 32u)
+                                                 uint32_t spread_below)
 {
     constexpr uint32_t kQ = RVPT_SORT_BINS + 1u;
     for (uint32_t k = threadIdx.x; k < kQ; k += blockDim.x)
@@ -819,7 +808,7 @@ __device__ __forceinline__ uint32_t prepare_wave(const FrameParams& p, WaveGroup
         const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
         /* spread: every warp gets one group even though each sub-queue rounds its last group up */
         const uint32_t share = n_warps > 2u * kQ ? n_warps - kQ : n_warps;
-        const uint32_t L = count <= spread_below ? max(1u, min(32u, (count + share - 1u) / share)) : big_group;
+        const uint32_t L = count <= spread_below ? max(1u, min(32u, (count + share - 1u) / share)) : 32u;
         uint32_t g = 0;
         for (uint32_t k = 0; k < kQ; ++k)
         {
@@ -1147,7 +1136,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             /* same scheme as the primary wave: the measured barrier wait of a 7/8-static wave
              * was three times that of the fully dynamic primary wave */
             g = resolve_claim(shard_ctr, groups, shard, claim);
-            if (g == 0xFFFFFFFFu) break;
+            if (warp_uniform(g == 0xFFFFFFFFu)) break;
             if (lane == 0) claim = atomicAdd(&shard_ctr[shard * 32u], 1u);
         }
         else if (round < static_rounds)
@@ -1156,7 +1145,7 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             break;
         else
             g = dyn_base + __shfl_sync(0xFFFFFFFFu, claim, 0);
-        if (g >= groups)
+        if (warp_uniform(g >= groups))
         {
             if (spread) continue; /* other warps of this round still have rays; warp-uniform */
             break;
@@ -1193,196 +1182,6 @@ __device__ __forceinline__ void bounce_phase(const FrameParams& p, const SceneVi
             if (!alive) finish_sample<kBatch>(p, slot, sample, s.rng);
         }
         if (!in_thread) push_survivors(p, qout, wc.qcount[b], alive, slot, s, sort);
-    }
-}
-
-/* ---- bounce waves of closed scenes: lanes refill themselves ------------------------------- */
-/* In a closed scene the rays a warp traces together need very different numbers of node steps
- * (Cornell box: 21 on average, 49 for the slowest of 32), so the node loop runs on 14 lanes of
- * 32 and the leaf block on 2 (`profiles/r02_k_frame_hot_blocks_cornell.txt`). Here a warp claims
- * RVPT_REFILL_RAYS rays at a time and splits the work into three passes:
- *   A  (all lanes) origin, direction, 1/direction and the octant's node array of every ray go to
- *      the warp's slab in shared memory;
- *   B  the walk: a lane whose ray is finished writes (clip distance, triangle) to the slab,
- *      takes the next ray of the slab (one shared-memory atomic) and walks on — nobody waits for
- *      the slowest ray until the slab runs dry; the path state is not live here;
- *   C  (all lanes) path state from the queue + hit from the slab: shading, parking, queueing.
- * Every ray is walked exactly as walk_nearest<.., kSorted> walks it, by whichever lane.
- * The slabs live in the origin-relative node copies, dead since the primary wave (a grid
- * barrier ago), and in the unused gap between the two halves of the node records. */
-#define RVPT_REFILL_RAYS 48u
-#define RVPT_REFILL_A_BYTES (32u * RVPT_REFILL_RAYS) /* (o.xyz, 1/d.x), (d.xyz, 1/d.y) */
-#define RVPT_REFILL_B_BYTES (16u * RVPT_REFILL_RAYS) /* (1/d.z, node array or 0, clip distance, triangle) */
-
-__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v)
-{
-    uint32_t r;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
-    return r;
-}
-
-/* does the scene leave room for the slabs? (block-uniform) */
-__device__ __forceinline__ bool refill_fits(const SceneViewT<true>& sc)
-{
-    const uint32_t rel_half = 8u * sc.oct_stride;                        /* one half of the eight relative copies */
-    const uint32_t gap = RVPT_OCT_B_OFFSET - 2u * rel_half;               /* behind the first halves */
-    return rel_half + gap >= (uint32_t)kWarpsPerCta * RVPT_REFILL_A_BYTES &&
-           rel_half >= (uint32_t)kWarpsPerCta * RVPT_REFILL_B_BYTES;
-}
-
-/* pass B for one warp: sa / sb = its slabs, n = rays in them, next = shared address of its counter */
-__device__ __forceinline__ void walk_refill(const SceneViewT<true>& sc, uint32_t sa, uint32_t sb, uint32_t n,
-                                            uint32_t next)
-{
-    uint32_t cur = threadIdx.x & 31u;
-    if (cur >= n) return;
-    uint32_t ra = sa + 32u * cur, rb = sb + 16u * cur;
-    float4 A = lds_f4_off<0>(ra), B = lds_f4_off<0>(rb);
-    float iy = __uint_as_float(ld_u32<true>(ra, 7u));
-    rv_f3 o = rv_make(A.x, A.y, A.z);
-    float ix = A.w, iz = B.x;
-    uint32_t nodes = __float_as_uint(B.y);
-    float best_t = RV_INF;
-    uint32_t best_tri = 0xFFFFFFFFu;
-    uint32_t node = nodes ? 0u : RVPT_NODE_END; /* 0: not a ray for the octant arrays, pass C traces it */
-    for (;;)
-    {
-        /* both branches end at the same join, once per iteration: the lanes that refilled test their
-         * first node together with everybody else's next node */
-        if (node == RVPT_NODE_END)
-        {
-            asm volatile("st.shared.v2.u32 [%0+8], {%1, %2};" ::"r"(rb), "r"(__float_as_uint(best_t)), "r"(best_tri)
-                         : "memory");
-            cur = atoms_add_u32(next, 1u);
-            if (cur >= n) break;
-            ra = sa + 32u * cur, rb = sb + 16u * cur;
-            A = lds_f4_off<0>(ra), B = lds_f4_off<0>(rb);
-            iy = __uint_as_float(ld_u32<true>(ra, 7u));
-            o = rv_make(A.x, A.y, A.z);
-            ix = A.w, iz = B.x;
-            nodes = __float_as_uint(B.y);
-            best_t = RV_INF, best_tri = 0xFFFFFFFFu;
-            node = nodes ? 0u : RVPT_NODE_END;
-        }
-        if (node != RVPT_NODE_END)
-        {
-            const uint32_t a = nodes + node * 16u;
-            const float4 n0 = lds_f4_off<0>(a);
-            const float4 n1 = lds_f4_off<RVPT_OCT_B_OFFSET>(a);
-            const float fx = (n0.y - o.x) * ix, nx = (n0.x - o.x) * ix;
-            const float fy = (n0.w - o.y) * iy, ny = (n0.z - o.y) * iy;
-            const float fz = (n1.y - o.z) * iz, nz = (n1.x - o.z) * iz;
-            const float t0 = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
-            const float t1 = fminf(fminf(fx, fy), fminf(fz, best_t));
-            const uint32_t skip = __float_as_uint(n1.z);
-            const uint32_t leaf = __float_as_uint(n1.w);
-            if (t1 >= t0)
-            {
-                if (!(leaf & RVPT_NODE_INNER))
-                {
-                    const float4 D = lds_f4_off<16>(ra);
-                    test_leaf<true, false, true>(sc, o, rv_make(D.x, D.y, D.z), leaf, best_t, best_tri);
-                    node = skip;
-                }
-                else
-                    node = node + 1;
-            }
-            else
-                node = skip;
-        }
-    }
-}
-
-template <bool kBatch>
-__device__ __forceinline__ void bounce_phase_refill(const FrameParams& p, const SceneViewT<true>& sc, int b,
-                                                    const WaveGroups& wg, bool sort, uint32_t* warp_next)
-{
-    WaveCounters& wc = p.ctr->wave;
-    const PathQueue qin = p.queue[(b - 1) & 1];
-    const PathQueue qout = p.queue[b & 1];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t* shard_ctr = wc.bounce_ctr[b & 1];
-    uint32_t shard = (blockIdx.x * (uint32_t)kWarpsPerCta + warp) % RVPT_CHUNK_SHARDS;
-    const uint32_t L = wg.L; /* RVPT_REFILL_RAYS (prepare_wave) */
-    const uint32_t groups = wg.pre[RVPT_SORT_BINS + 1u];
-    const uint32_t sa = (uint32_t)sc.oct_rel_nodes + warp * RVPT_REFILL_A_BYTES;
-    const uint32_t sb = (uint32_t)sc.oct_rel_nodes + RVPT_OCT_B_OFFSET + warp * RVPT_REFILL_B_BYTES;
-    const uint32_t next = smem_u32(&warp_next[warp]);
-
-    uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(&shard_ctr[shard * 32u], 1u);
-    for (;;)
-    {
-        const uint32_t g = resolve_claim(shard_ctr, groups, shard, claim);
-        if (g == 0xFFFFFFFFu) break;
-        if (lane == 0) claim = atomicAdd(&shard_ctr[shard * 32u], 1u);
-        uint32_t k = 0;
-#pragma unroll
-        for (uint32_t step = RVPT_SORT_BINS; step > 0; step >>= 1)
-            if (k + step <= RVPT_SORT_BINS && wg.pre[k + step] <= g) k += step;
-        const uint32_t i0 = (g - wg.pre[k]) * L;
-        const uint32_t n = min(L, wg.cnt[k] - i0);
-        const uint32_t qbase = k * p.bin_cap + i0;
-
-        /* pass A */
-        for (uint32_t j = lane; j < n; j += 32u)
-        {
-            const float4 a0 = __ldcs(&qin.q0[qbase + j]);
-            const float4 a1 = __ldcs(&qin.q1[qbase + j]);
-            /* intersect_aabb (intersection.glsl:327-357): invdir = 1/direction; see trace_nearest */
-            const float ix = 1.0f / a1.x, iy = 1.0f / a1.y, iz = 1.0f / a1.z;
-            const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
-            const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-            const uint32_t oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
-                                 ((__float_as_uint(iz) >> 31) << 2);
-            const uint32_t nodes = (lo > 0.0f && hi < RV_INF) ? (uint32_t)sc.oct_nodes + oct * sc.oct_stride : 0u;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 32u * j), "f"(a0.x), "f"(a0.y),
-                         "f"(a0.z), "f"(ix)
-                         : "memory");
-            asm volatile("st.shared.v4.f32 [%0+16], {%1, %2, %3, %4};" ::"r"(sa + 32u * j), "f"(a1.x), "f"(a1.y),
-                         "f"(a1.z), "f"(iy)
-                         : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + 16u * j), "f"(iz),
-                         "f"(__uint_as_float(nodes)), "f"(RV_INF), "f"(__uint_as_float(0xFFFFFFFFu))
-                         : "memory");
-        }
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&warp_next[warp]) = 32u;
-        __syncwarp();
-
-        /* pass B */
-        walk_refill(sc, sa, sb, n, next);
-        __syncwarp();
-
-        /* pass C */
-        for (uint32_t r = 0; r < n; r += 32u)
-        {
-            const uint32_t j = r + lane;
-            bool alive = false;
-            PathState s;
-            uint32_t slot = 0;
-            if (j < n)
-            {
-                load_path(qin, qbase + j, s, slot);
-                if constexpr (!kBatch) prefetch_prev(p, slot);
-                const float4 R = lds_f4_off<0>(sb + 16u * j);
-                float t = R.z;
-                uint32_t tri = __float_as_uint(R.w);
-                if (__float_as_uint(R.y) != 0u)
-                    settle_relaxed_hit(sc, s.o, s.d, t, tri);
-                else
-                    trace_nearest<true, false, true>(sc, s.o, s.d, t, tri);
-                rv_f3 sample;
-                alive = kajiya_shade<true>(sc, s, t, tri, sample);
-                if (alive && b == p.max_bounces - 1)
-                {
-                    alive = false; /* integrators.glsl:674-675: col is discarded */
-                    sample = rv_make(0.0f, 0.0f, 0.0f);
-                }
-                if (!alive) finish_sample<kBatch>(p, slot, sample, s.rng);
-            }
-            push_survivors(p, qout, wc.qcount[b], alive, slot, s, sort);
-        }
-        __syncwarp(); /* the slab is free again */
     }
 }
 
@@ -1598,7 +1397,6 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
     __shared__ unsigned long long small_waves;
     __shared__ uint32_t ordered_bounce; /* bounce rays walk the front-to-back arrays this frame */
     __shared__ WaveGroups wg;
-    __shared__ uint32_t warp_next[kWarpsPerCta]; /* bounce_phase_refill: next ray of each warp's slab */
     __shared__ float frame_consts[kBatch ? 3 * RVPT_MAX_BATCH : 1];
 
     stamp(p, 0);
@@ -1641,13 +1439,7 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
         grid.sync(); /* wave b-1 is complete: its survivor counts are final */
         stamp(p, 2 * b + 1);
         const uint32_t n_warps = gridDim.x * kWarpsPerCta;
-        const bool next_is_tail = b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull);
-        bool refill = false;
-        if constexpr (kSmem && kOct)
-            /* closed scene, a wave that goes back through the queue, room for the slabs */
-            refill = RVPT_REFILL_MODE != 0 && (RVPT_REFILL_MODE == 2 || ordered_bounce != 0u) && !next_is_tail &&
-                     refill_fits(sc);
-        const uint32_t count = prepare_wave(p, wg, wc.qcount[b - 1], 64u * n_warps, refill ? RVPT_REFILL_RAYS : 32u);
+        const uint32_t count = prepare_wave(p, wg, wc.qcount[b - 1], 64u * n_warps);
         if (count == 0)
         {
             synced = true;
@@ -1667,22 +1459,14 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
             for (uint32_t i = threadIdx.x; i < RVPT_CHUNK_SHARDS * 32u; i += blockDim.x)
                 wc.bounce_ctr[(b + 1) & 1][i] = 0u;
         const uint32_t deal = count <= 64u * n_warps ? RVPT_WAVE_SPREAD : RVPT_WAVE_SHARDED;
-        if (next_is_tail)
+        if (b + 1 < p.max_bounces && ((small_waves >> (b + 1)) & 1ull))
         {
             /* forecast: wave b+1 would be a tail anyway — its rays finish here, in their threads */
             bounce_phase<kSmem, kOct, true, kBatch>(p, sc, b, wg, deal, sort);
             stamp(p, 2 * b + 2);
             break;
         }
-        if constexpr (kSmem && kOct)
-        {
-            if (refill && deal == RVPT_WAVE_SHARDED)
-                bounce_phase_refill<kBatch>(p, sc, b, wg, sort, warp_next);
-            else
-                bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
-        }
-        else
-            bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
+        bounce_phase<kSmem, kOct, false, kBatch>(p, sc, b, wg, deal, sort);
         stamp(p, 2 * b + 2);
     }
     if constexpr (kBatch)
