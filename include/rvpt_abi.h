@@ -116,7 +116,7 @@ typedef struct rvpt_b200_stats
 #define RVPT_B200_EINVAL (-1)      /* bad argument */
 #define RVPT_B200_ECUDA (-2)       /* CUDA runtime error (see last_error) */
 #define RVPT_B200_ENOSCENE (-3)    /* render before upload_scene */
-#define RVPT_B200_EUNSUPPORTED (-4) /* valid in the reference, not built yet */
+#define RVPT_B200_EUNSUPPORTED (-4) /* beyond a limit of this engine (scene > 4 GiB, BVH deeper than the shader's 64-entry stack) */
 #define RVPT_B200_ENOMEM (-5)
 
 /* ------------------------------------------------------------------------ */

@@ -782,8 +782,74 @@ rv_f3 integrator_Cook(const Scene& sc, Ray ray, float mint, float maxt, int nbou
     return splat(0.0f);
 }
 
-/* compute_pass.comp:68-99. Mode 10+ (integrator_Hart, the sphere-tracing heat map of
- * distance_functions.glsl) is outside the hot-path scope: *ok = false. */
+/* distance_functions.glsl:36-61: distance from p to the triangle (a, b, c). sign() is
+ * GLSL.std.450 FSign (+1 / -1 / 0; NaN -> 0 as in oracle/spirv_vm.cpp), clamp() is FClamp =
+ * min(max(x, 0), 1), both arms of the ?: are pure, so which of them the binary evaluates
+ * does not matter. */
+float sign_of(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+float dot2(rv_f3 v) { return rv_dot(v, v); }
+
+float distance_triangle(rv_f3 p, rv_f3 a, rv_f3 b, rv_f3 c)
+{
+    const rv_f3 ba = rv_sub(b, a), pa = rv_sub(p, a);
+    const rv_f3 cb = rv_sub(c, b), pb = rv_sub(p, b);
+    const rv_f3 ac = rv_sub(a, c), pc = rv_sub(p, c);
+    const rv_f3 nor = rv_cross(ba, ac);
+    const float s0 = sign_of(rv_dot(rv_cross(ba, nor), pa));
+    const float s1 = sign_of(rv_dot(rv_cross(cb, nor), pb));
+    const float s2 = sign_of(rv_dot(rv_cross(ac, nor), pc));
+    float v;
+    if ((s0 + s1) + s2 < 2.0f)
+    {
+        const float e0 = dot2(rv_sub(rv_scale(clamp01(rv_dot(ba, pa) / dot2(ba)), ba), pa));
+        const float e1 = dot2(rv_sub(rv_scale(clamp01(rv_dot(cb, pb) / dot2(cb)), cb), pb));
+        const float e2 = dot2(rv_sub(rv_scale(clamp01(rv_dot(ac, pc) / dot2(ac)), ac), pc));
+        v = fminf(fminf(e0, e1), e2);
+    }
+    else
+    {
+        const float h = rv_dot(nor, pa);
+        v = (h * h) / dot2(nor);
+    }
+    return sqrtf(v);
+}
+
+/* distance_functions.glsl:70-116, sphere tracing against EVERY triangle in buffer order.
+ * MARCH_ITER 32, MARCH_EPS 0.1 (compute_pass.comp:10-11). Returns the iteration count, the
+ * only field integrator_Hart looks at. */
+int intersect_scene_st_iter(const Scene& sc, const Ray& ray, float mint, float maxt)
+{
+    float t = mint;
+    rv_f3 p = rv_add(ray.origin, rv_scale(t, ray.direction));
+    int i;
+    for (i = 0; i < 32; ++i)
+    {
+        float t_radius = INF; /* t_radius_idx.x; the index lane never reaches the output */
+        for (size_t j = 0; j < sc.n_tris; ++j)
+        {
+            const rvpt_triangle& tri = sc.tris[j];
+            const float dist = distance_triangle(p, rv_make(tri.vertex0[0], tri.vertex0[1], tri.vertex0[2]),
+                                                 rv_make(tri.vertex1[0], tri.vertex1[1], tri.vertex1[2]),
+                                                 rv_make(tri.vertex2[0], tri.vertex2[1], tri.vertex2[2]));
+            t_radius = t_radius < dist ? t_radius : dist; /* min_idx :63-66: lhs.x < rhs.x ? lhs : rhs */
+        }
+        const float min_radius = fminf(INF, t_radius); /* min(s_radius_idx.x, t_radius_idx.x), s = INF */
+        if (min_radius < 0.1f || min_radius > maxt) return i;
+        t = t + min_radius;
+        p = rv_add(p, rv_scale(min_radius, ray.direction));
+    }
+    return i;
+}
+
+/* integrators.glsl:681-693: the sphere tracer's iteration count as a grey level, iter / 31
+ * (32 / 31 when the march ran out of iterations). */
+rv_f3 integrator_Hart(const Scene& sc, const Ray& ray, float mint, float maxt)
+{
+    return splat((float)intersect_scene_st_iter(sc, ray, mint, maxt) / 31.0f);
+}
+
+/* compute_pass.comp:68-99: every index outside 0..9 (negative ones too) is integrator_Hart. */
 rv_f3 eval_integrator(const Scene& sc, int idx, const Ray& ray, int max_bounces, uint32_t* rng,
                       Counters* ctr, bool* ok)
 {
@@ -799,12 +865,12 @@ rv_f3 eval_integrator(const Scene& sc, int idx, const Ray& ray, int max_bounces,
         case 7: return integrator_Whitted(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
         case 8: return integrator_Cook(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
         case 9: return integrator_Kajiya(sc, ray, 0.0f, INF, max_bounces, rng, ctr);
-        default: *ok = false; return splat(0.0f);
+        default: (void)ok; return integrator_Hart(sc, ray, 0.0f, INF);
     }
 }
 
-/* compute_pass.comp:121-167 for one pixel. Returns false for an integrator
- * this oracle does not restate (mode 10+, Hart's sphere tracer). */
+/* compute_pass.comp:121-167 for one pixel. (The bool result is a leftover of the time when
+ * integrator_Hart was not restated: every integrator index is now.) */
 bool shade_pixel(const Scene& sc, const Frame& fr, uint32_t x, uint32_t y, rv_f3 prev_in,
                  rv_f3* out, Counters* ctr)
 {

@@ -221,6 +221,9 @@ struct FrameParams
     float sort_lo[3];             /* scene bounding box (root node) */
     float sort_scale[3];          /* cells per unit: (1 << RVPT_SORT_CELL_BITS) / extent */
     unsigned long long* timeline; /* optional [n_ctas][RVPT_TIMELINE_SLOTS] globaltimer stamps */
+    /* integrator_Hart (render mode 10) only: the caller's 64-byte triangle records in upload order */
+    const float4* raw_tris;
+    uint32_t n_raw_tris;
 };
 
 #endif

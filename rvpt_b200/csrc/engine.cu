@@ -69,6 +69,14 @@ struct rvpt_b200_ctx
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
     bool have_scene = false;
+    /* integrator_Hart (render mode 10) marches against the caller's vertices, not the packed
+     * records: the 64-byte triangles in the order the shader's buffer holds them (the caller's, or
+     * BVH-permuted when the BVH was built here), copied to the device the first time a frame asks
+     * for that integrator */
+    std::vector<rvpt_triangle> raw_sorted; /* only when upload_scene built the BVH itself */
+    float4* d_raw_tris = nullptr;
+    size_t raw_capacity = 0;   /* triangles d_raw_tris can hold */
+    bool raw_valid = false;    /* d_raw_tris holds the current scene */
 
     /* frame buffers (tile layout) */
     void* d_accum = nullptr;      /* own allocation */
@@ -697,6 +705,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_scene);
+        cudaFree(ctx->d_raw_tris);
         if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
         ctx->d_scene = nullptr;
         ctx->h_scene_pinned = nullptr;
@@ -921,6 +930,8 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
             return 0;
         }
         ctx->scene_blob_bytes = 0; /* invalid until this upload succeeds */
+        ctx->raw_valid = false;
+        ctx->raw_sorted.clear();
         ctx->scene_inputs.resize(hdr + nb + tb + mb);
         std::memcpy(ctx->scene_inputs.data(), counts, hdr);
         if (nb) std::memcpy(ctx->scene_inputs.data() + hdr, nodes, nb);
@@ -944,6 +955,7 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
         for (size_t i = 0; i < n_triangles; ++i) sorted[i] = triangles[perm[i]];
         rc = pack_scene(ctx, built.data(), n_built, sorted.data(), n_triangles, materials,
                         n_materials, false, ps);
+        ctx->raw_sorted.swap(sorted);
     }
     else
         rc = pack_scene(ctx, nodes, n_nodes, triangles, n_triangles, materials, n_materials, brute,
@@ -960,6 +972,39 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
 
 namespace
 {
+
+/* The caller's triangle records on the device, for integrator_Hart. */
+int ensure_raw_triangles(rvpt_b200_ctx* ctx)
+{
+    if (ctx->raw_valid) return 0;
+    const rvpt_triangle* src = nullptr;
+    size_t n = 0;
+    if (!ctx->raw_sorted.empty())
+        src = ctx->raw_sorted.data(), n = ctx->raw_sorted.size();
+    else
+    {
+        /* scene_inputs = [3 counts][nodes][triangles][materials] of the last upload */
+        size_t counts[3];
+        std::memcpy(counts, ctx->scene_inputs.data(), sizeof(counts));
+        const size_t nb = counts[0] == (size_t)-1 ? 0 : counts[0] * sizeof(rvpt_bvh_node);
+        src = reinterpret_cast<const rvpt_triangle*>(ctx->scene_inputs.data() + sizeof(counts) + nb);
+        n = counts[1];
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (n > ctx->raw_capacity)
+    {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_raw_tris);
+        ctx->d_raw_tris = nullptr;
+        ctx->raw_capacity = 0;
+        CU(cudaMalloc(&ctx->d_raw_tris, n * sizeof(rvpt_triangle)));
+        ctx->raw_capacity = n;
+    }
+    /* pageable source: the copy is staged before the call returns, in stream order on the device */
+    CU(cudaMemcpyAsync(ctx->d_raw_tris, src, n * sizeof(rvpt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->raw_valid = true;
+    return 0;
+}
 
 /* One frame (n_batch == 0: every aa pass, plus the other integrators' pixels) or one batched
  * launch covering frames current_frame .. current_frame + n_batch - 1 (aa == 1, Kajiya only). */
@@ -1082,6 +1127,14 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     if (!all_kajiya && p.n_chunks > 0)
     {
         /* pixels of the other integrators (split view / debug views): one in-thread pass */
+        bool hart = false;
+        for (int m : modes) hart = hart || m < 0 || m > 9;
+        if (hart)
+        {
+            if ((rc = ensure_raw_triangles(ctx))) return rc;
+            p.raw_tris = ctx->d_raw_tris;
+            p.n_raw_tris = (uint32_t)ctx->layout.n_tris;
+        }
         p.pass = 0;
         ScopedTimer tm(ctx, 1);
         CU(rvpt::launch_modes(p, ctx->scene_smem, ctx->grid_primary, ctx->stream));
@@ -1106,14 +1159,9 @@ int validate_frame(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const flo
         return fail(ctx, RVPT_B200_EINVAL, "max_bounces = %d outside [0,64]", rs->max_bounces);
     const int modes[4] = {rs->top_left_render_mode, rs->top_right_render_mode,
                           rs->bottom_left_render_mode, rs->bottom_right_render_mode};
-    for (int m : modes)
-    {
-        /* eval_integrator's default case is integrator_Hart, the sphere-tracing heat map of
-         * distance_functions.glsl (compute_pass.comp:96-97) — outside the hot-path scope */
-        if (m < 0 || m > 9)
-            return fail(ctx, RVPT_B200_EUNSUPPORTED,
-                        "render mode %d (integrator_Hart sphere tracer) is not built; modes 0-9 are", m);
-    }
+    /* every index outside 0..9 is eval_integrator's default case, integrator_Hart
+     * (compute_pass.comp:96-97): one distance evaluation per triangle and march step */
+    (void)modes;
     return 0;
 }
 

@@ -1805,6 +1805,57 @@ __device__ rv_f3 eval_mode(const SceneViewT<kSmem>& sc, int mode, rv_f3 o, rv_f3
     return splat3(1.0f * fmaxf(0.0f, rv_dot(light_dir, n)));
 }
 
+/* Mode 10 and every other index outside 0..9: integrator_Hart (integrators.glsl:681-693), the
+ * sphere tracer of distance_functions.glsl:70-116 shown as a heat map of its iteration count.
+ * It marches against EVERY triangle of the buffer (no BVH), so it reads the caller's vertices —
+ * p.raw_tris, the 64-byte records in upload order — through the read-only path: all lanes of a
+ * warp ask for the same address, one broadcast transaction per record. */
+__device__ __forceinline__ float sign_glsl(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+/* distance_functions.glsl:36-61 (squared distance; the caller takes the root) */
+__device__ __forceinline__ float distance_triangle_sq(rv_f3 p, rv_f3 a, rv_f3 b, rv_f3 c)
+{
+    const rv_f3 ba = rv_sub(b, a), pa = rv_sub(p, a);
+    const rv_f3 cb = rv_sub(c, b), pb = rv_sub(p, b);
+    const rv_f3 ac = rv_sub(a, c), pc = rv_sub(p, c);
+    const rv_f3 nor = rv_cross(ba, ac);
+    const float side = (sign_glsl(rv_dot(rv_cross(ba, nor), pa)) + sign_glsl(rv_dot(rv_cross(cb, nor), pb))) +
+                       sign_glsl(rv_dot(rv_cross(ac, nor), pc));
+    if (side < 2.0f)
+    {
+        const rv_f3 q0 = rv_sub(rv_scale(clamp01(rv_dot(ba, pa) / rv_dot(ba, ba)), ba), pa);
+        const rv_f3 q1 = rv_sub(rv_scale(clamp01(rv_dot(cb, pb) / rv_dot(cb, cb)), cb), pb);
+        const rv_f3 q2 = rv_sub(rv_scale(clamp01(rv_dot(ac, pc) / rv_dot(ac, ac)), ac), pc);
+        return fminf(fminf(rv_dot(q0, q0), rv_dot(q1, q1)), rv_dot(q2, q2));
+    }
+    const float h = rv_dot(nor, pa);
+    return (h * h) / rv_dot(nor, nor);
+}
+
+__device__ __noinline__ rv_f3 integrator_hart(const FrameParams& p, rv_f3 o, rv_f3 d)
+{
+    const float4* __restrict__ T = p.raw_tris;
+    rv_f3 pos = rv_add(o, rv_scale(0.0f, d)); /* p = origin + mint * direction, mint = 0 */
+    int i = 0;
+    for (; i < 32; ++i) /* MARCH_ITER, compute_pass.comp:10 */
+    {
+        float radius = RV_INF;
+        for (uint32_t j = 0; j < p.n_raw_tris; ++j)
+        {
+            const float4 a = __ldg(T + 4 * j), b = __ldg(T + 4 * j + 1), c = __ldg(T + 4 * j + 2);
+            const float dist = sqrtf(distance_triangle_sq(pos, rv_make(a.x, a.y, a.z), rv_make(b.x, b.y, b.z),
+                                                          rv_make(c.x, c.y, c.z)));
+            radius = radius < dist ? radius : dist; /* min_idx: lhs.x < rhs.x ? lhs : rhs */
+        }
+        radius = fminf(RV_INF, radius);
+        if (radius < 0.1f || radius > RV_INF) break; /* MARCH_EPS; maxt = INF */
+        pos = rv_add(pos, rv_scale(radius, d));
+    }
+    const float g = (float)i / 31.0f;
+    return rv_make(g, g, g);
+}
+
 template <bool kSmem>
 __global__ void __launch_bounds__(kThreads) k_modes(const FrameParams p)
 {
@@ -1840,7 +1891,8 @@ __global__ void __launch_bounds__(kThreads) k_modes(const FrameParams p)
             cy = 1.0f - cy;
             rv_f3 o, d;
             camera_ray(p, cx, cy, o, d);
-            sum = rv_add(sum, eval_mode<kSmem>(sc, mode, o, d, p.max_bounces, &rng));
+            sum = rv_add(sum, (mode >= 0 && mode <= 8) ? eval_mode<kSmem>(sc, mode, o, d, p.max_bounces, &rng)
+                                                       : integrator_hart(p, o, d));
         }
         accumulate_pixel(p, slot, rv_make(sum.x / p.aa_f, sum.y / p.aa_f, sum.z / p.aa_f), y * p.W + x);
     }

@@ -327,8 +327,8 @@ def test_unsupported_and_error_paths(rv, builtin):
     assert e.value.code == -3  # no scene
     eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
     with pytest.raises(rv.EngineError) as e:
-        eng.render_frame(rv.default_settings(mode=10), rv.camera_data())
-    assert e.value.code == -4  # integrator_Hart (sphere tracer) is out of scope
+        eng.render_frame(rv.default_settings(aa=0), rv.camera_data())
+    assert e.value.code == -1  # the reference divides by aa
     bad = builtin.triangles.copy()
     bad["material_id"][5, 0] = 7
     with pytest.raises(rv.EngineError):
@@ -431,6 +431,67 @@ def test_other_integrators_bit_exact(rv, oracle_mod, cornell, mode):
     same = (g.view(np.uint32) == o.view(np.uint32)) | (np.isnan(g) & np.isnan(o))
     assert same.all(), f"mode {mode}: {(~same).sum()} words differ"
     assert np.array_equal(eng.read_output_rgba8(), ora.result)
+
+
+@pytest.mark.parametrize("mode", [10, 11, -1])
+def test_hart_sphere_tracer_bit_exact(rv, oracle_mod, cornell, builtin, mode):
+    """f-3, eval_integrator's default case (compute_pass.comp:96-97): integrator_Hart
+    (integrators.glsl:681-693), the sphere tracer of distance_functions.glsl:36-116 as a heat map
+    of its iteration count — every index outside 0..9. Cornell box with aa = 2 over two frames,
+    the built-in scene from a pose that sees background, silhouette and surface; then the paths
+    that hand the kernel its vertices differently: BVH built inside upload_scene (triangles
+    permuted there), the brute-force flag, a second upload on the same engine, a 2-way partition."""
+    eng, ora, _ = _render_both(rv, oracle_mod, cornell, 112, 80, CORNELL_POSE, frames=2, fov=60.0, mode=mode, aa=2)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"Hart, mode {mode}, Cornell")
+    assert np.array_equal(eng.read_output_rgba8(), ora.result)
+    levels = np.unique(np.rint(ora.accum[..., 0] * 31 * 2))  # mean of 2 x 2 samples of k/31
+    assert len(levels) > 8 and ora.accum[..., 0].max() > 1.0  # 32/31: marches that ran out of iterations
+    if mode != 10:
+        return
+    W, H = 96, 64
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    rs = rv.default_settings(mode=10)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+    ora.render_frame(rs, cam)
+    # the oracle marches the triangles in buffer order; min() over them is order-independent
+    # on these scenes (no NaN distances), so the caller's order and the permuted one agree
+    for flags, nodes, tris in ((0, builtin.nodes, builtin.triangles), (0, None, builtin.scene.triangles),
+                               (0x4, None, builtin.scene.triangles)):  # 0x4 = RVPT_B200_FLAG_BRUTE_FORCE
+        eng = rv.Engine(W, H, flags=flags)
+        eng.upload_scene(cornell.triangles, cornell.materials, cornell.nodes)
+        eng.render_frame(rs, rv.camera_data(translation=CORNELL_POSE, aspect=W / H, fov=60.0))  # another scene first
+        eng.upload_scene(tris, builtin.materials, nodes)
+        eng.reset_accum()
+        eng.render_frame(rs, cam)
+        _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"Hart, built-in scene, flags {flags}, nodes {nodes is not None}")
+        eng.close()
+    img = np.zeros((H, W, 4), np.float32)
+    for r in range(2):
+        e = rv.Engine(W, H, rank=r, nranks=2)
+        e.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+        e.render_frame(rs, cam)
+        img += e.read_accum_f32()  # disjoint supports
+        e.close()
+    _assert_bit_equal(img, ora.accum, "Hart, 2-way partition")
+
+
+def test_split_view_with_hart_quadrants(rv, oracle_mod, builtin):
+    """Kajiya pixels on the wavefront path, Utah and two Hart quadrants (indices 10 and -3) in
+    k_modes, progressive over two frames."""
+    W, H = 160, 96
+    cam = rv.camera_data(translation=PINNED_POSE, aspect=W / H)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, builtin.nodes)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, builtin.nodes)
+    for f in range(2):
+        rs = rv.default_settings(frame=f)
+        rs["top_left_render_mode"], rs["top_right_render_mode"] = 10, 9
+        rs["bottom_left_render_mode"], rs["bottom_right_render_mode"] = -3, 4
+        rs["split_ratio"] = (0.45, 0.5)
+        eng.render_frame(rs, cam)
+        ora.render_frame(rs, cam)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "split view with Hart")
+    assert eng.stats()["active"] == ora.active_list()
 
 
 def test_split_view_four_integrators(rv, oracle_mod, builtin):

@@ -249,10 +249,29 @@ def test_running_mean_and_rgba8_store(oracle_mod, rv, builtin):
     assert not q.result[..., 3].any()  # alpha = 0 (compute_pass.comp:165-166)
 
 
-def test_unsupported_integrator_is_reported(oracle_mod, rv, builtin):
-    o = oracle_mod.OracleRenderer(16, 16, builtin.triangles, builtin.materials, builtin.nodes)
-    with pytest.raises(RuntimeError):  # mode 10+: integrator_Hart, the sphere tracer (out of scope)
-        o.render_frame(rv.default_settings(mode=10), rv.camera_data())
+def test_hart_sphere_tracer_known_answers(oracle_mod, rv):
+    """integrator_Hart (integrators.glsl:681-693) = iterations of the sphere tracer / 31
+    (distance_functions.glsl:70-116, MARCH_ITER 32, MARCH_EPS 0.1), worked by hand on one large
+    triangle in the plane z = 5 seen by an orthographic camera looking down +z from the origin:
+    a ray over the triangle's interior steps the full distance 5 in iteration 0 and stops in
+    iteration 1 (radius 0 < 0.1) -> 1/31; index 10, 11 and -1 all select it
+    (compute_pass.comp:96-97). A ray that starts 0.05 above a triangle stops in iteration 0 -> 0.
+    The same triangle behind the camera: the distance only grows, the march runs out -> 32/31."""
+    mats = rv.make_material((1, 1, 1, 0))
+    W = H = 8
+
+    def render(z, mode):
+        tri = rv.make_triangles([[-50.0, -50.0, z]], [[50.0, -50.0, z]], [[0.0, 80.0, z]], 0)
+        nodes, perm = rv.build_bvh(tri)
+        o = oracle_mod.OracleRenderer(W, H, tri[perm], mats, nodes)
+        # ortho camera (camera.glsl:55-76): parallel rays along the camera's +z, scale 1
+        o.render_frame(rv.default_settings(mode=mode, camera_mode=1), rv.camera_data(aspect=1.0, scale=1.0))
+        return o.accum[..., :3]
+
+    for mode in (10, 11, -1):
+        assert np.array_equal(render(5.0, mode), np.full((H, W, 3), np.float32(1.0) / np.float32(31.0), np.float32))
+    assert not render(0.05, 10).any()
+    assert np.array_equal(render(-5.0, 10), np.full((H, W, 3), np.float32(32.0) / np.float32(31.0), np.float32))
 
 
 def test_debug_integrators_sanity(oracle_mod, rv, builtin):
