@@ -165,6 +165,11 @@ typedef struct rvpt_b200_stats
 /* rvpt_b200_upload_scene(nodes == NULL) builds its BVH on the GPU (rvpt_b200_build_bvh_gpu)
  * instead of on the host (rvpt_b200_build_bvh). */
 #define RVPT_B200_FLAG_GPU_BVH 0x400u
+/* Batched launches (rvpt_b200_render_frames) normally render their primary wave pixel block by
+ * pixel block with a per-block list of candidate leaves (kernels.cu, primary_phase_beam); this
+ * flag makes every primary ray walk the tree instead. Same results; for A/B measurements and
+ * cross-checks. */
+#define RVPT_B200_FLAG_NO_LEAF_LISTS 0x800u
 
 typedef struct rvpt_b200_ctx rvpt_b200_ctx;
 

@@ -24,6 +24,7 @@ FLAG_REFERENCE_ORDER = 0x80
 FLAG_NO_QUEUE_SORT = 0x100
 FLAG_NO_BATCH = 0x200
 FLAG_GPU_BVH = 0x400
+FLAG_NO_LEAF_LISTS = 0x800
 
 OK, EINVAL, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
 

@@ -224,6 +224,10 @@ struct FrameParams
     /* integrator_Hart (render mode 10) only: the caller's 64-byte triangle records in upload order */
     const float4* raw_tris;
     uint32_t n_raw_tris;
+    /* batched launches of shared-memory scenes with octant arrays, pinhole camera: frames per
+     * (pixel block, frame group) unit of the primary wave (kernels.cu, primary_phase_beam); 0 = the
+     * primary wave walks the tree for every ray */
+    uint32_t frame_group;
 };
 
 #endif

@@ -68,6 +68,8 @@ struct rvpt_b200_ctx
     SceneLayout layout{};
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
+    bool scene_nested = false; /* every child box lies inside its parent's, all bounds finite (leaf lists) */
+    uint32_t frame_group = 16; /* frames per (pixel block, frame group) unit of a batched primary wave; 0: off */
     bool have_scene = false;
     /* integrator_Hart (render mode 10) marches against the caller's vertices, not the packed
      * records: the 64-byte triangles in the order the shader's buffer holds them (the caller's, or
@@ -338,6 +340,7 @@ struct PackedScene
 {
     bool bounds_ordered = true; /* every node has min <= max on every axis (no NaN) */
     bool coincident_faces = false; /* has_coincident_faces(): the walk order can decide a hit */
+    bool boxes_nested = false;     /* boxes_are_nested(): a ray that enters a leaf box enters every ancestor's */
     std::vector<DevNode> nodes;
     std::vector<DevTri> tris;
     std::vector<uint32_t> meta;
@@ -661,6 +664,30 @@ void apply_scene_l2_policy(rvpt_b200_ctx* ctx)
     cudaGetLastError(); /* best effort */
 }
 
+/* Every child box inside its parent's box and every bound finite — what a builder produces, but
+ * not something the reference's node format promises. The batched primary wave's leaf lists
+ * (kernels.cu, build_leaf_list) skip the inner nodes, which is only the walk's result when a ray
+ * that passes a leaf's slab test passes every ancestor's. */
+bool boxes_are_nested(const std::vector<DevNode>& nodes)
+{
+    auto inside = [](const DevNode& c, const DevNode& p) {
+        return c.bmin_x >= p.bmin_x && c.bmax_x <= p.bmax_x && c.bmin_y >= p.bmin_y && c.bmax_y <= p.bmax_y &&
+               c.bmin_z >= p.bmin_z && c.bmax_z <= p.bmax_z;
+    };
+    for (size_t i = 0; i < nodes.size(); ++i)
+    {
+        const DevNode& n = nodes[i];
+        const float b[6] = {n.bmin_x, n.bmax_x, n.bmin_y, n.bmax_y, n.bmin_z, n.bmax_z};
+        for (float v : b)
+            if (!std::isfinite(v)) return false;
+        if (!(n.leaf_first & RVPT_NODE_INNER)) continue;
+        const size_t c1 = i + 1, c2 = n.leaf_first & ~RVPT_NODE_INNER;
+        if (c1 >= nodes.size() || c2 >= nodes.size()) return false;
+        if (!inside(nodes[c1], n) || !inside(nodes[c2], n)) return false;
+    }
+    return true;
+}
+
 int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
 {
     SceneLayout L{};
@@ -705,7 +732,6 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_scene);
-        cudaFree(ctx->d_raw_tris);
         if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
         ctx->d_scene = nullptr;
         ctx->h_scene_pinned = nullptr;
@@ -741,6 +767,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
                             oct == ctx->scene_oct;
     ctx->layout = L;
     ctx->scene_oct = oct;
+    ctx->scene_nested = oct && boxes_are_nested(ps.nodes);
     if (!same_shape)
     {
         ctx->scene_smem =
@@ -806,10 +833,12 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (flags & ~(RVPT_B200_FLAG_ACCUM_RGBA8 | RVPT_B200_FLAG_REFERENCE_DISPATCH |
                   RVPT_B200_FLAG_BRUTE_FORCE | RVPT_B200_FLAG_UNFUSED | RVPT_B200_FLAG_NO_OCTANTS |
                   RVPT_B200_FLAG_NO_BATCH | RVPT_B200_FLAG_NO_FORECAST | RVPT_B200_FLAG_REFERENCE_ORDER |
-                  RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_GPU_BVH))
+                  RVPT_B200_FLAG_NO_QUEUE_SORT | RVPT_B200_FLAG_GPU_BVH | RVPT_B200_FLAG_NO_LEAF_LISTS))
         return fail(ctx, RVPT_B200_EINVAL, "unknown flags 0x%x", flags);
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RVPT_B200_FRAME_GROUP")) /* developer knob (tuning runs); 0 = no leaf lists */
+        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
     if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
         ctx->queue_budget = (size_t)std::max(1, std::atoi(e)) << 20;
     ctx->device = device;
@@ -859,6 +888,7 @@ extern "C" void rvpt_b200_destroy(rvpt_b200_ctx* ctx)
         free_frame_buffers(ctx);
         cudaFree(ctx->d_timeline);
         cudaFree(ctx->d_scene);
+        cudaFree(ctx->d_raw_tris);
         if (ctx->h_scene_pinned) cudaFreeHost(ctx->h_scene_pinned);
         if (ctx->scene_copied) cudaEventDestroy(ctx->scene_copied);
         for (auto& t : ctx->timed) ctx->event_pool.push_back(t);
@@ -1083,6 +1113,11 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.bin_cap = ctx->bin_cap;
     for (int a = 0; a < 3; ++a) p.sort_lo[a] = ctx->sort_lo[a], p.sort_scale[a] = ctx->sort_scale[a];
     p.n_batch = n_batch;
+    /* batched primary wave by (pixel block, frame group) with per-block leaf lists: octant arrays in
+     * shared memory, pinhole camera (one origin, directions affine in the pixel), nested boxes */
+    p.frame_group = (n_batch > 0 && ctx->scene_smem && ctx->scene_oct && ctx->scene_nested && rs->camera_mode == 0 &&
+                     !(ctx->flags & RVPT_B200_FLAG_NO_LEAF_LISTS))
+                        ? ctx->frame_group : 0u;
     p.samples = ctx->d_samples;
     p.sample_stride = ctx->n_local_padded * RVPT_TILE_PIXELS;
 

@@ -183,6 +183,9 @@ struct SceneViewT
     addr_t oct_nodes;
     addr_t oct_rel_nodes;
     uint32_t oct_stride;
+    /* kOct only: 64 bytes per warp in the unused gap between the two halves of the octant arrays
+     * (0 when the gap is too small): the leaf list of the pixel block a warp is rendering */
+    addr_t beam_scratch;
 };
 
 template <bool kSmem, typename A>
@@ -243,6 +246,7 @@ __device__ __forceinline__ SceneViewT<kSmem> make_view(const unsigned char* base
     v.oct_nodes = 0;
     v.oct_rel_nodes = 0;
     v.oct_stride = 0;
+    v.beam_scratch = 0;
     return v;
 }
 
@@ -415,6 +419,7 @@ __device__ __noinline__ uint2 retrace_reference_order(uint32_t nodes, uint32_t t
     sc.nodes = nodes, sc.tris = tris, sc.meta = meta, sc.mats = 0;
     sc.rel_nodes = sc.rel_num = sc.oct_nodes = sc.oct_rel_nodes = 0;
     sc.oct_stride = 0;
+    sc.beam_scratch = 0;
     const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
     float t = RV_INF;
     uint32_t tri = 0xFFFFFFFFu;
@@ -625,13 +630,24 @@ struct PathState
 
 /* Returns true if the path continues (state updated), false if it ended with
  * `sample`. */
+template <bool kSmem>
+__device__ __forceinline__ bool kajiya_shade(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample, float t,
+                                             uint32_t tri);
+
 template <bool kSmem, bool kRel, bool kOct>
 __device__ __forceinline__ bool kajiya_step(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample)
 {
     float t;
     uint32_t tri;
     trace_nearest<kSmem, kRel, kOct>(sc, s.o, s.d, t, tri);
+    return kajiya_shade<kSmem>(sc, s, sample, t, tri);
+}
 
+/* everything of the iteration behind intersect_scene: (t, tri) = the nearest hit, tri = 0xFFFFFFFF: none */
+template <bool kSmem>
+__device__ __forceinline__ bool kajiya_shade(const SceneViewT<kSmem>& sc, PathState& s, rv_f3& sample, float t,
+                                             uint32_t tri)
+{
     if (tri == 0xFFFFFFFFu)
     {
         /* :578-579 background */
@@ -1065,6 +1081,250 @@ __device__ __forceinline__ uint32_t resolve_claim(uint32_t* ctr, uint32_t n_unit
     return unit;
 }
 
+/* ---- primary wave of a batched launch, one pixel block for several frames --------------- */
+
+/* The primary rays of one 8x4 pixel block form a thin beam from the camera origin, the same beam
+ * in every frame of a batch (only the jitter inside each pixel changes). build_leaf_list()
+ * collects — once per (pixel block, group of frames) — the leaves whose boxes ANY ray of that beam
+ * can enter, in the order of the beam's octant array, into 32 u16 entries of shared memory per
+ * warp; the rays of the block then test exactly those leaf boxes, with the walk's own slab
+ * arithmetic, instead of walking the tree.
+ *
+ * Why this is the walk's result bit for bit: a leaf box lies inside every ancestor's box (the
+ * host checks it, SceneLayout::nested), subtraction and multiplication by one invdir are
+ * monotonic under rounding, and max / min are monotonic, so for a given ray and clip distance
+ *   t0(ancestor) <= t0(leaf)  and  t1(ancestor) >= t1(leaf):
+ * a ray that passes a leaf's slab test passes the test of every ancestor, and a leaf whose
+ * ancestor fails fails itself. The walk therefore tests the triangles of exactly the leaves
+ * whose OWN box passes, in array order — which is what the list loop does, with the same clip
+ * evolution (same leaves, same order), the same relaxed bookkeeping and the same re-trace.
+ *
+ * Why the list is complete: it is built by interval arithmetic over the beam — directions are
+ * affine in the pixel coordinate before normalisation (camera.glsl:41-47) and the slab test's
+ * outcome does not depend on the length of the direction, so per axis |d| ranges over the
+ * corner values; a box is dropped only if the LARGEST possible exit distance lies below the
+ * SMALLEST possible entry distance, after widening every quantity by 1e-5 of its scale (the
+ * rays' own rounding errors are below 1e-6 of it). Anything unusual — a direction component
+ * that changes sign inside the block, more than 32 leaves, a ray outside its beam's octant —
+ * takes the ordinary walk. */
+#define RVPT_NO_LIST 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t build_leaf_list(const FrameParams& p, const SceneViewT<true>& sc, uint32_t x0,
+                                                    uint32_t y0, uint32_t scratch, uint32_t& base_out,
+                                                    uint32_t& oct_out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    base_out = 0u, oct_out = 0u;
+    /* pixel block [x0, x0 + 8] x [y0, y0 + 4] (jitter in [0, 1], rand() may return 1), a 64th of a
+     * pixel wider on every side; compute_pass.comp:153-154, camera.glsl:41-43 */
+    const float pad = 0.015625f;
+    const float cxa = ((float)x0 - pad) * p.inv_dim_x, cxb = ((float)x0 + (8.0f + pad)) * p.inv_dim_x;
+    const float cya = 1.0f - ((float)y0 - pad) * p.inv_dim_y, cyb = 1.0f - ((float)y0 + (4.0f + pad)) * p.inv_dim_y;
+    const float ua = p.aspect * ((cxa + cxa) - 1.0f), ub = p.aspect * ((cxb + cxb) - 1.0f);
+    const float va = (cya + cya) - 1.0f, vb = (cyb + cyb) - 1.0f;
+    float dlo[3], dhi[3], L = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        const float a = p.cam[i] * ua, b = p.cam[i] * ub, c = p.cam[4 + i] * va, e = p.cam[4 + i] * vb;
+        const float wz = p.cam[8 + i] * p.inv_tan_half_fov;
+        dlo[i] = (fminf(a, b) + fminf(c, e)) + wz;
+        dhi[i] = (fmaxf(a, b) + fmaxf(c, e)) + wz;
+        L += fmaxf(fabsf(dlo[i]), fabsf(dhi[i]));
+    }
+    if (!(L > 0.0f && L < 1e30f)) return RVPT_NO_LIST;
+    const float widen = 1e-5f * L, apart = 1e-4f * L;
+    uint32_t oct = 0u;
+    float inv_lo[3], inv_hi[3];
+    uint32_t flip[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        const float lo = dlo[i] - widen, hi = dhi[i] + widen;
+        const bool neg = hi < -apart;
+        if (!(neg || lo > apart)) return RVPT_NO_LIST; /* the component changes sign (or nearly) inside the block */
+        const float alo = neg ? -hi : lo, ahi = neg ? -lo : hi;
+        inv_lo[i] = (1.0f / ahi) * 0.99999f;
+        inv_hi[i] = (1.0f / alo) * 1.00001f;
+        flip[i] = neg ? 0x80000000u : 0u;
+        oct |= neg ? (1u << i) : 0u;
+    }
+    const uint32_t base = (uint32_t)sc.oct_rel_nodes + oct * sc.oct_stride;
+    base_out = base, oct_out = oct;
+
+    /* entry / exit bounds of the beam for one record of that array */
+    auto beam_misses = [&](const float4& n0, const float4& n1, float eps) -> bool
+    {
+        const float nn[3] = {__uint_as_float(__float_as_uint(n0.x) ^ flip[0]) - eps,
+                             __uint_as_float(__float_as_uint(n0.z) ^ flip[1]) - eps,
+                             __uint_as_float(__float_as_uint(n1.x) ^ flip[2]) - eps};
+        const float nf[3] = {__uint_as_float(__float_as_uint(n0.y) ^ flip[0]) + eps,
+                             __uint_as_float(__float_as_uint(n0.w) ^ flip[1]) + eps,
+                             __uint_as_float(__float_as_uint(n1.y) ^ flip[2]) + eps};
+        float t0 = 0.0f, t1 = RV_INF;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+            t0 = fmaxf(t0, fminf(nn[i] * inv_lo[i], nn[i] * inv_hi[i]));
+            t1 = fminf(t1, fmaxf(nf[i] * inv_lo[i], nf[i] * inv_hi[i]));
+        }
+        return t1 < t0;
+    };
+
+    /* the root first: most pixel blocks of an open scene see no geometry at all */
+    const float4 r0 = lds_f4_off<0>(base), r1 = lds_f4_off<RVPT_OCT_B_OFFSET>(base);
+    const float R = fmaxf(fmaxf(fmaxf(fabsf(r0.x), fabsf(r0.y)), fmaxf(fabsf(r0.z), fabsf(r0.w))),
+                          fmaxf(fabsf(r1.x), fabsf(r1.y)));
+    if (!(R < 1e30f)) return RVPT_NO_LIST;
+    const float eps = 1e-5f * R;
+    if (beam_misses(r0, r1, eps)) return 0u;
+
+    uint32_t count = 0u;
+    const uint32_t n_nodes = p.layout.n_nodes;
+    for (uint32_t j0 = 0u; j0 < n_nodes; j0 += 32u)
+    {
+        const uint32_t j = j0 + lane;
+        const uint32_t a = base + min(j, n_nodes - 1u) * 16u;
+        const float4 n0 = lds_f4_off<0>(a), n1 = lds_f4_off<RVPT_OCT_B_OFFSET>(a);
+        const bool pass = j < n_nodes && !(__float_as_uint(n1.w) & RVPT_NODE_INNER) && !beam_misses(n0, n1, eps);
+        const uint32_t hits = __ballot_sync(0xFFFFFFFFu, pass);
+        const uint32_t pos = count + (uint32_t)__popc(hits & ((1u << lane) - 1u));
+        if (pass && pos < 32u)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(scratch + 2u * pos), "h"((unsigned short)(j * 16u)) : "memory");
+        count += (uint32_t)__popc(hits);
+    }
+    __syncwarp();
+    return count > 32u ? RVPT_NO_LIST : count;
+}
+
+/* The rays of a listed pixel block: slab test of every listed leaf box + its triangles, in list
+ * (= array) order. Same arithmetic as walk_nearest<true, true, true>; best_t is the clip distance
+ * of the relaxed walk. */
+__device__ __forceinline__ void trace_listed(const SceneViewT<true>& sc, uint32_t base, uint32_t scratch,
+                                             uint32_t n_list, rv_f3 o, rv_f3 d, float ix, float iy, float iz,
+                                             float& best_t, uint32_t& best_tri)
+{
+#ifdef RVPT_PROBE_NO_RELAXED
+    constexpr bool kRelaxed = false;
+#else
+    constexpr bool kRelaxed = true;
+#endif
+    for (uint32_t k = 0u; k < n_list; ++k)
+    {
+        unsigned short off;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(off) : "r"(scratch + 2u * k));
+        const uint32_t a = base + (uint32_t)off;
+        const float4 n0 = lds_f4_off<0>(a), n1 = lds_f4_off<RVPT_OCT_B_OFFSET>(a);
+        const float fx = n0.y * ix, nx = n0.x * ix;
+        const float fy = n0.w * iy, ny = n0.z * iy;
+        const float fz = n1.y * iz, nz = n1.x * iz;
+        const float t0 = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+        const float t1 = fminf(fminf(fx, fy), fminf(fz, best_t));
+        if (t1 >= t0) test_leaf<true, true, kRelaxed>(sc, o, d, __float_as_uint(n1.w), best_t, best_tri);
+    }
+}
+
+/* primary_phase for batched launches of scenes with octant arrays and a pinhole camera
+ * (p.frame_group > 0): a claimed unit is (pixel block, group of frame_group consecutive frames).
+ * What depends on the pixel block only — pixel coordinates, the RNG seed's hash, the leaf list —
+ * is computed once per unit. */
+__device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const SceneViewT<true>& sc, bool sort)
+{
+    WaveCounters& wc = p.ctr->wave;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long traced = 0;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t G = p.frame_group;
+    const uint32_t n_groups = (p.n_batch + G - 1u) / G;
+    const uint32_t n_units = p.n_chunks * n_groups;
+    const uint32_t scratch = (uint32_t)sc.beam_scratch + (threadIdx.x >> 5) * 64u;
+    const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
+    uint32_t shard = gwarp % RVPT_CHUNK_SHARDS;
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
+    for (;;)
+    {
+        const uint32_t unit = resolve_claim(wc.chunk_ctr, n_units, shard, claim);
+        if (unit == 0xFFFFFFFFu) break;
+        if (lane == 0) claim = atomicAdd(&wc.chunk_ctr[shard * 32u], 1u);
+
+        const uint32_t g = div_magic(unit, p.n_chunks, p.n_chunks_magic);
+        const uint32_t c = unit - g * p.n_chunks;
+        const uint32_t slot = c * 32u + lane;
+        uint32_t x, y;
+        slot_to_xy(p, slot, x, y);
+        const bool inside = (x < p.W_eff) && (y < p.H_eff) && ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
+        const uint32_t seed = rv_wang_hash(x + y * p.W) + p.frame; /* util.glsl:35-36, + frame_in_batch below */
+        const uint32_t fi_end = min(g * G + G, p.n_batch);
+        if (p.max_bounces > 0)
+            traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside)) * (fi_end - g * G);
+
+        __syncwarp(); /* nobody still reads the previous unit's list */
+        uint32_t base, oct;
+        const uint32_t n_list = build_leaf_list(p, sc, x - (lane & 7u), y - (lane >> 3), scratch, base, oct);
+
+        for (uint32_t fi = g * G; fi < fi_end; ++fi)
+        {
+            const uint32_t tag = slot | (fi << RVPT_BATCH_SLOT_BITS);
+            bool alive = false;
+            PathState s;
+            if (inside)
+            {
+                s.rng = seed + fi;
+                /* compute_pass.comp:153-154 */
+                const float jx = rv_rand(&s.rng);
+                const float jy = rv_rand(&s.rng);
+                const float cx = ((float)x + jx) * p.inv_dim_x;
+                float cy = ((float)y + jy) * p.inv_dim_y;
+                cy = 1.0f - cy;
+                camera_ray(p, cx, cy, s.o, s.d);
+                s.thr = rv_make(1.0f, 1.0f, 1.0f);
+                s.col = rv_make(0.0f, 0.0f, 0.0f);
+
+                rv_f3 sample = rv_make(0.0f, 0.0f, 0.0f);
+                if (p.max_bounces > 0)
+                {
+                    float t = RV_INF;
+                    uint32_t tri = 0xFFFFFFFFu;
+                    const float ix = 1.0f / s.d.x, iy = 1.0f / s.d.y, iz = 1.0f / s.d.z;
+                    const uint32_t my_oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
+                                            ((__float_as_uint(iz) >> 31) << 2);
+                    const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
+                    const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
+                    if (n_list != RVPT_NO_LIST && my_oct == oct && lo > 0.0f && hi < RV_INF)
+                    {
+                        trace_listed(sc, base, scratch, n_list, o, s.d, ix, iy, iz, t, tri);
+#ifndef RVPT_PROBE_NO_RELAXED
+                        if (tri != 0xFFFFFFFFu)
+                        {
+                            if (hit_is_ambiguous(tri))
+                            {
+                                const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, s.d);
+                                t = __uint_as_float(r.x), tri = r.y;
+                            }
+                            else
+                                t = exact_of(t);
+                        }
+#endif
+                    }
+                    else
+                        trace_nearest<true, true, true>(sc, s.o, s.d, t, tri);
+                    alive = kajiya_shade<true>(sc, s, sample, t, tri);
+                    if (alive && p.max_bounces == 1)
+                    {
+                        alive = false; /* :674-675 ran out of iterations */
+                        sample = rv_make(0.0f, 0.0f, 0.0f);
+                    }
+                }
+                if (!alive) finish_sample<true>(p, tag, sample, s.rng, y * p.W + x);
+            }
+            push_survivors(p, p.queue[0], wc.qcount[0], alive, tag, s, sort);
+        }
+    }
+    if (lane == 0 && traced) atomicAdd(&p.ctr->stats.active[0], traced);
+}
+
+
 __device__ __forceinline__ void load_path(const PathQueue& q, uint32_t i, PathState& s,
                                           uint32_t& slot)
 {
@@ -1284,6 +1544,9 @@ __device__ __forceinline__ SceneViewT<kSmem> setup_scene(const FrameParams& p, u
             sc.oct_nodes = smem_u32(oct);
             sc.oct_rel_nodes = smem_u32(oct_rel);
             sc.oct_stride = n_nodes * 16u;
+            /* the first halves of the 16 copies end at n_nodes * 256 bytes, the second halves start
+             * RVPT_OCT_B_OFFSET bytes in: what lies between is allocated and unused */
+            sc.beam_scratch = n_nodes * 256u + kWarpsPerCta * 64u <= RVPT_OCT_B_OFFSET ? smem_u32(oct) + n_nodes * 256u : 0u;
         }
         else if constexpr (kRel)
         {
@@ -1429,7 +1692,17 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
      * octant x origin cell; ordered_bounce is visible to everybody since the barriers of
      * setup_scene */
     const bool sort = p.bin_cap != 0u && ordered_bounce != 0u;
-    primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
+    bool listed = false;
+    if constexpr (kSmem && kRel && kOct && kBatch) listed = p.frame_group != 0u && sc.beam_scratch != 0u;
+    if constexpr (kSmem && kRel && kOct && kBatch)
+    {
+        if (listed)
+            primary_phase_beam(p, sc, sort);
+        else
+            primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
+    }
+    else
+        primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
     stamp(p, 2);
 
     WaveCounters& wc = p.ctr->wave;
