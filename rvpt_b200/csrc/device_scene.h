@@ -57,8 +57,10 @@ struct DevNode
  *   b = n.xyz,  A00              n = cross(e0,e1), A00 = dot(e1,e1)
  *   c = e0.xyz, A01              A01 = A10 = -dot(e0,e1)
  *   d = e1.xyz, A11              A11 = dot(e0,e0)
- * Records are stored leaf by leaf in walk order; meta[i] = material index |
- * RVPT_TRI_LAST on the last triangle of a leaf.
+ * Records are stored leaf by leaf in walk order. A second, 16-byte record per triangle
+ * (DevTriMeta) holds what shading needs of the hit triangle — normalize(n) of intersect_scene
+ * (intersection.glsl:511), evaluated once at upload with rv_normalize — and meta = material
+ * index | RVPT_TRI_LAST on the last triangle of a leaf.
  */
 struct DevTri
 {
@@ -66,6 +68,12 @@ struct DevTri
     float nx, ny, nz, a00;
     float e0x, e0y, e0z, a01;
     float e1x, e1y, e1z, a11;
+};
+
+struct DevTriMeta
+{
+    float unx, uny, unz; /* rv_normalize(n) */
+    uint32_t meta;       /* material index | RVPT_TRI_LAST */
 };
 
 /* Material, 3 x float4 (convert_old_material, intersection.glsl:45-57). */
@@ -80,7 +88,7 @@ struct DevMaterial
 /*
  * The whole scene is one contiguous 16-byte-aligned blob so one TMA bulk copy
  * (cp.async.bulk) stages it into shared memory:
- *   [DevNode x n_nodes][DevTri x n_tris][meta u32 x n_tris (padded)][DevMaterial x n_mats]
+ *   [DevNode x n_nodes][DevTri x n_tris][DevTriMeta x n_tris][DevMaterial x n_mats]
  *   [ordered octant node arrays, optional]
  */
 struct SceneLayout

@@ -69,7 +69,8 @@ struct rvpt_b200_ctx
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
     bool scene_nested = false; /* every child box lies inside its parent's, all bounds finite (leaf lists) */
-    uint32_t frame_group = 16; /* frames per (pixel block, frame group) unit of a batched primary wave; 0: off */
+    uint32_t frame_group = 32; /* most frames per (pixel block, frame group) unit of a batched primary wave; 0: off */
+    bool frame_group_fixed = false; /* RVPT_B200_FRAME_GROUP: use exactly that many */
     bool have_scene = false;
     /* integrator_Hart (render mode 10) marches against the caller's vertices, not the packed
      * records: the 64-byte triangles in the order the shader's buffer holds them (the caller's, or
@@ -343,7 +344,7 @@ struct PackedScene
     bool boxes_nested = false;     /* boxes_are_nested(): a ray that enters a leaf box enters every ancestor's */
     std::vector<DevNode> nodes;
     std::vector<DevTri> tris;
-    std::vector<uint32_t> meta;
+    std::vector<DevTriMeta> meta;
     std::vector<DevMaterial> mats;
 };
 
@@ -404,7 +405,10 @@ int pack_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* nodes, size_t n_nodes,
             out.tris.push_back(make_dev_tri(tris[first + k]));
             uint32_t m = (uint32_t)(int)tris[first + k].material_id[0];
             if (k + 1 == count) m |= RVPT_TRI_LAST;
-            out.meta.push_back(m);
+            /* intersect_scene's normalize(n) (intersection.glsl:511) depends on the triangle only */
+            const DevTri& t = out.tris.back();
+            const rv_f3 un = rv_normalize(rv_make(t.nx, t.ny, t.nz));
+            out.meta.push_back(DevTriMeta{un.x, un.y, un.z, m});
         }
     };
 
@@ -699,7 +703,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
     L.off_tris = (uint32_t)off;
     off = align16(off + ps.tris.size() * sizeof(DevTri));
     L.off_meta = (uint32_t)off;
-    off = align16(off + ps.meta.size() * sizeof(uint32_t));
+    off = align16(off + ps.meta.size() * sizeof(DevTriMeta));
     L.off_mats = (uint32_t)off;
     off = align16(off + ps.mats.size() * sizeof(DevMaterial));
     if (off > 0xFFFFFFF0u) return fail(ctx, RVPT_B200_EUNSUPPORTED, "scene larger than 4 GiB");
@@ -719,7 +723,7 @@ int upload_packed(rvpt_b200_ctx* ctx, const PackedScene& ps)
         std::memcpy(blob.data() + L.off_oct, oct_block.data(), oct_block.size() * sizeof(float));
     std::memcpy(blob.data(), ps.nodes.data(), ps.nodes.size() * sizeof(DevNode));
     std::memcpy(blob.data() + L.off_tris, ps.tris.data(), ps.tris.size() * sizeof(DevTri));
-    std::memcpy(blob.data() + L.off_meta, ps.meta.data(), ps.meta.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + L.off_meta, ps.meta.data(), ps.meta.size() * sizeof(DevTriMeta));
     std::memcpy(blob.data() + L.off_mats, ps.mats.data(), ps.mats.size() * sizeof(DevMaterial));
 
     CU(cudaSetDevice(ctx->device));
@@ -838,7 +842,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RVPT_B200_FRAME_GROUP")) /* developer knob (tuning runs); 0 = no leaf lists */
-        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
+        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e))), ctx->frame_group_fixed = true;
     if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
         ctx->queue_budget = (size_t)std::max(1, std::atoi(e)) << 20;
     ctx->device = device;
@@ -1118,6 +1122,15 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.frame_group = (n_batch > 0 && ctx->scene_smem && ctx->scene_oct && ctx->scene_nested && rs->camera_mode == 0 &&
                      !(ctx->flags & RVPT_B200_FLAG_NO_LEAF_LISTS))
                         ? ctx->frame_group : 0u;
+    if (p.frame_group && !ctx->frame_group_fixed)
+    {
+        /* a list is built once per unit, so long groups are cheaper (C2: 16 frames 28.9, 32 frames
+         * 29.4, 64 frames 30.2 Gsamples/s) — until the units get too few to balance the warps
+         * (sparse poses, tile partitions): at least six units per resident warp */
+        const uint64_t want = 6ull * (uint64_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32);
+        while (p.frame_group > 4u && (uint64_t)p.n_chunks * ((n_batch + p.frame_group - 1u) / p.frame_group) < want)
+            p.frame_group >>= 1;
+    }
     p.samples = ctx->d_samples;
     p.sample_stride = ctx->n_local_padded * RVPT_TILE_PIXELS;
 

@@ -166,7 +166,7 @@ struct SceneViewT
     typedef typename std::conditional<kSmem, uint32_t, uintptr_t>::type addr_t;
     addr_t nodes; /* 2 float4 per node */
     addr_t tris;  /* 4 float4 per triangle */
-    addr_t meta;  /* u32 per triangle */
+    addr_t meta;  /* float4 per triangle: unit normal, material index | RVPT_TRI_LAST */
     addr_t mats;  /* 3 float4 per material */
     /* primary-wave copies relative to the shared camera origin (kRel only):
      * node bounds minus origin, and dot(v0 - origin, n) per triangle — the
@@ -291,7 +291,7 @@ __device__ __forceinline__ void test_leaf(const SceneViewT<kSmem>& sc, rv_f3 o, 
     {
         const float4 A = ld_f4<kSmem>(sc.tris, 4 * i + 0);
         const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
-        m = ld_u32<kSmem>(sc.meta, i);
+        m = ld_u32<kSmem>(sc.meta, 4u * i + 3u);
         const float num = kRel ? __uint_as_float(ld_u32<kSmem>(sc.rel_num, i))
                                : rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
                                         rv_make(B.x, B.y, B.z));
@@ -657,14 +657,14 @@ __device__ __forceinline__ bool kajiya_shade(const SceneViewT<kSmem>& sc, PathSt
         return false;
     }
 
-    const float4 B = ld_f4<kSmem>(sc.tris, 4 * tri + 1);
-    const uint32_t mi = ld_u32<kSmem>(sc.meta, tri) & ~RVPT_TRI_LAST;
+    const float4 U = ld_f4<kSmem>(sc.meta, tri);
+    const uint32_t mi = __float_as_uint(U.w) & ~RVPT_TRI_LAST;
     const float4 M0 = ld_f4<kSmem>(sc.mats, 3 * mi + 0);
     const float4 M1 = ld_f4<kSmem>(sc.mats, 3 * mi + 1);
     const int type = __float_as_int(M1.w);
 
-    /* intersect_scene (intersection.glsl:511-513) */
-    rv_f3 normal = rv_normalize(rv_make(B.x, B.y, B.z));
+    /* intersect_scene (intersection.glsl:511-513): normalize(n), evaluated at upload */
+    rv_f3 normal = rv_make(U.x, U.y, U.z);
     const rv_f3 pos = rv_add(s.o, rv_scale(t, s.d));
 
     /* :582 */
@@ -1286,29 +1286,32 @@ __device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const S
                 {
                     float t = RV_INF;
                     uint32_t tri = 0xFFFFFFFFu;
-                    const float ix = 1.0f / s.d.x, iy = 1.0f / s.d.y, iz = 1.0f / s.d.z;
-                    const uint32_t my_oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
-                                            ((__float_as_uint(iz) >> 31) << 2);
-                    const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
-                    const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-                    if (n_list != RVPT_NO_LIST && my_oct == oct && lo > 0.0f && hi < RV_INF)
+                    if (n_list != 0u) /* an empty list: no ray of this block enters the root box */
                     {
-                        trace_listed(sc, base, scratch, n_list, o, s.d, ix, iy, iz, t, tri);
-#ifndef RVPT_PROBE_NO_RELAXED
-                        if (tri != 0xFFFFFFFFu)
+                        const float ix = 1.0f / s.d.x, iy = 1.0f / s.d.y, iz = 1.0f / s.d.z;
+                        const uint32_t my_oct = (__float_as_uint(ix) >> 31) | ((__float_as_uint(iy) >> 31) << 1) |
+                                                ((__float_as_uint(iz) >> 31) << 2);
+                        const float lo = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
+                        const float hi = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
+                        if (n_list != RVPT_NO_LIST && my_oct == oct && lo > 0.0f && hi < RV_INF)
                         {
-                            if (hit_is_ambiguous(tri))
+                            trace_listed(sc, base, scratch, n_list, o, s.d, ix, iy, iz, t, tri);
+#ifndef RVPT_PROBE_NO_RELAXED
+                            if (tri != 0xFFFFFFFFu)
                             {
-                                const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, s.d);
-                                t = __uint_as_float(r.x), tri = r.y;
+                                if (hit_is_ambiguous(tri))
+                                {
+                                    const uint2 r = retrace_reference_order(sc.nodes, sc.tris, sc.meta, o, s.d);
+                                    t = __uint_as_float(r.x), tri = r.y;
+                                }
+                                else
+                                    t = exact_of(t);
                             }
-                            else
-                                t = exact_of(t);
-                        }
 #endif
+                        }
+                        else
+                            trace_nearest<true, true, true>(sc, s.o, s.d, t, tri);
                     }
-                    else
-                        trace_nearest<true, true, true>(sc, s.o, s.d, t, tri);
                     alive = kajiya_shade<true>(sc, s, sample, t, tri);
                     if (alive && p.max_bounces == 1)
                     {
@@ -1843,7 +1846,7 @@ __device__ __forceinline__ bool trace_any(const SceneViewT<kSmem>& sc, rv_f3 o, 
                     const float4 B = ld_f4<kSmem>(sc.tris, 4 * i + 1);
                     const float4 C = ld_f4<kSmem>(sc.tris, 4 * i + 2);
                     const float4 D = ld_f4<kSmem>(sc.tris, 4 * i + 3);
-                    m = ld_u32<kSmem>(sc.meta, i);
+                    m = ld_u32<kSmem>(sc.meta, 4u * i + 3u);
                     const float num = rv_dot(rv_make(A.x - o.x, A.y - o.y, A.z - o.z),
                                              rv_make(B.x, B.y, B.z));
                     const float den = rv_dot(d, rv_make(B.x, B.y, B.z));
@@ -1894,11 +1897,11 @@ __device__ __forceinline__ HitInfo intersect_scene_dev(const SceneViewT<kSmem>& 
     h.type = -1;
     if (h.hit)
     {
-        const float4 B = ld_f4<kSmem>(sc.tris, 4 * tri + 1);
-        const uint32_t mi = ld_u32<kSmem>(sc.meta, tri) & ~RVPT_TRI_LAST;
+        const float4 U = ld_f4<kSmem>(sc.meta, tri);
+        const uint32_t mi = __float_as_uint(U.w) & ~RVPT_TRI_LAST;
         const float4 M0 = ld_f4<kSmem>(sc.mats, 3 * mi + 0);
         const float4 M1 = ld_f4<kSmem>(sc.mats, 3 * mi + 1);
-        h.normal = rv_normalize(rv_make(B.x, B.y, B.z));
+        h.normal = rv_make(U.x, U.y, U.z);
         h.pos = rv_add(o, rv_scale(h.t, d));
         h.base_color = rv_make(M0.x, M0.y, M0.z);
         h.ior = M0.w;

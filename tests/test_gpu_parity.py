@@ -775,6 +775,69 @@ def test_batched_launch_bit_exact(rv, oracle_mod, builtin, cornell, case):
         assert eng.stats()["frames"] == 35
 
 
+def test_leaf_lists_of_the_batched_primary_wave(rv, oracle_mod, builtin, cornell):
+    """Batched launches render their primary wave pixel block by pixel block: per 8x4 block the
+    leaves its beam can enter are listed once and the block's rays of a whole group of frames
+    test those leaf boxes instead of walking the tree (kernels.cu, primary_phase_beam). The list
+    must be complete and the result the walk's, bit for bit: against the oracle and against the
+    same engine with RVPT_B200_FLAG_NO_LEAF_LISTS, for poses that exercise every branch —
+    camera inside the scene box, far away (a block sees more than 32 leaves: ordinary walk),
+    rotated (blocks whose direction components change sign: ordinary walk), grazing along a wall,
+    wide and narrow fields of view, ragged images, frame groups that do not divide the batch,
+    a tile partition — and for a BVH whose boxes are NOT nested (a child box grown beyond its
+    parent's: legal in the reference's format, lists must switch themselves off)."""
+    from rvpt_b200 import _lib
+    cases = [
+        (builtin, 320, 180, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 90.0, 19),
+        (builtin, 256, 144, (0.0, 0.8, -2.5), (0.0, 0.0, 0.0), 90.0, 33),
+        (builtin, 200, 120, (0.0, 1.0, -14.0), (0.0, 0.0, 0.0), 30.0, 17),    # tiny bunny: > 32 leaves per block
+        (builtin, 208, 120, (0.6, 0.9, -1.2), (0.3, -0.5, 0.2), 120.0, 16),    # rotated, wide
+        (builtin, 97, 61, (-0.4, 0.4, 0.9), (0.1, 2.6, 0.0), 70.0, 7),
+        (cornell, 240, 136, (0.0, 1.2, -3.4), (0.0, 0.0, 0.0), 60.0, 18),
+        (cornell, 160, 96, (0.95, 0.05, -0.9), (0.02, -0.1, 0.0), 100.0, 16),   # grazing along wall and floor
+        (cornell, 160, 96, (0.0, 1.0, 0.0), (1.3, 0.4, 0.0), 150.0, 5),        # inside the box
+    ]
+    for prep, W, H, pose, rot, fov, n in cases:
+        cam = rv.camera_data(translation=pose, rotation=rot, aspect=W / H, fov=fov)
+        ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+        for f in range(n):
+            ora.render_frame(rv.default_settings(frame=f), cam)
+        for flags in (0, _lib.FLAG_NO_LEAF_LISTS):
+            eng = rv.Engine(W, H, flags=flags)
+            eng.upload_scene(prep.triangles, prep.materials, prep.nodes)
+            eng.render_frames(rv.default_settings(frame=0), cam, n)
+            assert eng.stats()["kernel_launches"] == 1
+            _assert_bit_equal(eng.read_accum_f32(), ora.accum, f"pose {pose} rot {rot} fov {fov} flags {flags:#x}")
+            eng.close()
+    # tile partition: the blocks of a rank are the same blocks
+    prep, W, H, pose, rot, fov, n = cases[3]
+    cam = rv.camera_data(translation=pose, rotation=rot, aspect=W / H, fov=fov)
+    ora = oracle_mod.OracleRenderer(W, H, prep.triangles, prep.materials, prep.nodes)
+    for f in range(n):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+    img = np.zeros((H, W, 4), np.float32)
+    for r in range(3):
+        e = rv.Engine(W, H, rank=r, nranks=3)
+        e.upload_scene(prep.triangles, prep.materials, prep.nodes)
+        e.render_frames(rv.default_settings(frame=0), cam, n)
+        img += e.read_accum_f32()
+        e.close()
+    _assert_bit_equal(img, ora.accum, "leaf lists, 3-way partition")
+    # boxes that are not nested: grow one leaf's box far beyond its parent's
+    nodes = builtin.nodes.copy()
+    leaf = int(np.flatnonzero(nodes["primitive_count"] > 0)[7])
+    nodes["bounds"][leaf] += np.array([-3, 3, -3, 3, -3, 3], np.float32)
+    W, H, n = 192, 112, 9
+    cam = rv.camera_data(translation=(0.0, 0.8, -2.5), aspect=W / H)
+    ora = oracle_mod.OracleRenderer(W, H, builtin.triangles, builtin.materials, nodes)
+    for f in range(n):
+        ora.render_frame(rv.default_settings(frame=f), cam)
+    eng = rv.Engine(W, H)
+    eng.upload_scene(builtin.triangles, builtin.materials, nodes)
+    eng.render_frames(rv.default_settings(frame=0), cam, n)
+    _assert_bit_equal(eng.read_accum_f32(), ora.accum, "boxes not nested")
+
+
 def test_batched_launch_partition_and_large_scene(rv, oracle_mod, builtin):
     """Batches on a 3-way tile partition (ragged image) reassemble the oracle's image; a scene on
     the global-memory path batches too; NO_BATCH is the same computation frame by frame."""

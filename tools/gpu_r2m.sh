@@ -1,0 +1,24 @@
+#!/bin/bash
+# unit normals precomputed per triangle + no inverse direction for blocks with an empty leaf list + adaptive
+# frame groups, against the previous commit's library (rvpt_b200/variants/libprev.so) on ONE box.
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -q -x ) > gpurun_out/r2m_tests.log 2>&1
+grep -E "passed|failed|error|real|differ" gpurun_out/r2m_tests.log | tail -8
+run() { tag=$1; shift; env "$@" timeout 600 python bench.py $ARGS --no-cpu-baseline --no-c4 > gpurun_out/bench_r2m_$tag.json 2> gpurun_out/bench_r2m_$tag.err; }
+PREV=$PWD/rvpt_b200/variants/libprev.so
+for w in builtin pinned cornell mesh500k tridel; do
+  case $w in builtin) ARGS="";; pinned) ARGS="--pose pinned";; cornell) ARGS="--scene cornell --steps 5";;
+    tridel) ARGS="--scene tridel --frames 16 --steps 3";; mesh500k) ARGS="--scene mesh --mesh-tris 500000 --frames 16 --steps 3";; esac
+  run ${w}_new A=1
+  run ${w}_prev RVPT_B200_LIB=$PREV
+  case $w in builtin|pinned|cornell) run ${w}_prev_g32 RVPT_B200_LIB=$PREV RVPT_B200_FRAME_GROUP=32; run ${w}_new_g64 RVPT_B200_FRAME_GROUP=64;; esac
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/bench_r2m_*.json")):
+    try:
+        d = json.loads([l for l in open(f) if l.startswith("{")][-1])
+        print(f.split("r2m_")[1][:-5], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "parity", d["parity_ok"], "ms/launch", round(d["roofline"]["ms_per_launch"], 3))
+    except Exception as e:
+        print(f, "failed", e)
+PY
