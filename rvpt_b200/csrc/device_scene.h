@@ -31,6 +31,9 @@
 #define RVPT_MAX_BATCH 64u          /* frames per launch (6 tag bits) */
 /* octant node copies in shared memory: byte distance between the two float4 halves of a record */
 #define RVPT_OCT_B_OFFSET (100u * 1024u)
+#define RVPT_MAX_GROUPS 27 /* frame groups of a batched primary wave (FrameParams::group_start) */
+#define RVPT_LIST_WORDS 36u /* u16 per pixel block in FrameParams::leaf_lists */
+#define RVPT_LIST_NONE 0xFFFFu /* no list for this block: its rays walk the tree */
 #define RVPT_TIMELINE_SLOTS 16u     /* per-CTA phase stamps of the last frame kernel */
 
 /*
@@ -232,10 +235,15 @@ struct FrameParams
     /* integrator_Hart (render mode 10) only: the caller's 64-byte triangle records in upload order */
     const float4* raw_tris;
     uint32_t n_raw_tris;
-    /* batched launches of shared-memory scenes with octant arrays, pinhole camera: frames per
-     * (pixel block, frame group) unit of the primary wave (kernels.cu, primary_phase_beam); 0 = the
-     * primary wave walks the tree for every ray */
-    uint32_t frame_group;
+    /* batched launches of shared-memory scenes with octant arrays, pinhole camera: a first phase
+     * lists, per 8x4 pixel block, the leaves the block's beam of primary rays can enter
+     * (leaf_lists: RVPT_LIST_WORDS u16 per block: count or RVPT_LIST_NONE, octant, 2 unused, 32
+     * node offsets), and the primary wave claims (pixel block, frame group) units (kernels.cu,
+     * primary_phase_beam); group g covers the frames group_start[g] .. group_start[g + 1] - 1 of
+     * the batch. n_groups == 0: the primary wave walks the tree for every ray. */
+    uint32_t n_groups;
+    uint8_t group_start[RVPT_MAX_GROUPS + 1];
+    unsigned short* leaf_lists;
 };
 
 #endif

@@ -69,8 +69,7 @@ struct rvpt_b200_ctx
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
     bool scene_nested = false; /* every child box lies inside its parent's, all bounds finite (leaf lists) */
-    uint32_t frame_group = 32; /* most frames per (pixel block, frame group) unit of a batched primary wave; 0: off */
-    bool frame_group_fixed = false; /* RVPT_B200_FRAME_GROUP: use exactly that many */
+    uint32_t frame_group = 8; /* frames per (pixel block, frame group) unit of a batched primary wave; 0: no leaf lists */
     bool have_scene = false;
     /* integrator_Hart (render mode 10) marches against the caller's vertices, not the packed
      * records: the 64-byte triangles in the order the shader's buffer holds them (the caller's, or
@@ -101,6 +100,7 @@ struct rvpt_b200_ctx
     bool copy_pending = false;
     float4* d_carry = nullptr;      /* allocated on first aa > 1 */
     float4* d_samples = nullptr;    /* batched launches: [batch_cap][slots] parked samples */
+    unsigned short* d_leaf_lists = nullptr; /* batched launches: RVPT_LIST_WORDS u16 per 8x4 pixel block, on first use */
     PathQueue queue[2]{};
     FrameCounters* d_ctr = nullptr;
     void* d_scratch = nullptr; /* raster-sized float4 staging for read-backs */
@@ -185,6 +185,8 @@ void free_frame_buffers(rvpt_b200_ctx* ctx)
     cudaFree(ctx->d_carry);
     cudaFree(ctx->d_ctr);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_leaf_lists);
+    ctx->d_leaf_lists = nullptr;
     free_queues(ctx);
     ctx->d_accum = ctx->d_out_tiles = nullptr;
     ctx->accum = ctx->out_tiles = nullptr;
@@ -842,7 +844,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RVPT_B200_FRAME_GROUP")) /* developer knob (tuning runs); 0 = no leaf lists */
-        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e))), ctx->frame_group_fixed = true;
+        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
     if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
         ctx->queue_budget = (size_t)std::max(1, std::atoi(e)) << 20;
     ctx->device = device;
@@ -1119,17 +1121,25 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
     p.n_batch = n_batch;
     /* batched primary wave by (pixel block, frame group) with per-block leaf lists: octant arrays in
      * shared memory, pinhole camera (one origin, directions affine in the pixel), nested boxes */
-    p.frame_group = (n_batch > 0 && ctx->scene_smem && ctx->scene_oct && ctx->scene_nested && rs->camera_mode == 0 &&
-                     !(ctx->flags & RVPT_B200_FLAG_NO_LEAF_LISTS))
-                        ? ctx->frame_group : 0u;
-    if (p.frame_group && !ctx->frame_group_fixed)
+    p.n_groups = 0;
+    p.leaf_lists = nullptr;
+    if (n_batch > 0 && ctx->scene_smem && ctx->scene_oct && ctx->scene_nested && rs->camera_mode == 0 &&
+        ctx->frame_group && p.n_chunks > 0 && !(ctx->flags & RVPT_B200_FLAG_NO_LEAF_LISTS))
     {
-        /* a list is built once per unit, so long groups are cheaper (C2: 16 frames 28.9, 32 frames
-         * 29.4, 64 frames 30.2 Gsamples/s) — until the units get too few to balance the warps
-         * (sparse poses, tile partitions): at least six units per resident warp */
-        const uint64_t want = 6ull * (uint64_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32);
-        while (p.frame_group > 4u && (uint64_t)p.n_chunks * ((n_batch + p.frame_group - 1u) / p.frame_group) < want)
-            p.frame_group >>= 1;
+        /* Leaf lists: built once per launch by its first phase, used by (pixel block, frame group)
+         * units. Groups are short — the wave ends when its last units end (with 32-frame groups one
+         * rank of eight waited 64 us of a 330 us primary wave for them), and all a longer group saves
+         * is the per-unit pixel arithmetic. */
+        if (!ctx->d_leaf_lists)
+            CU(cudaMalloc(&ctx->d_leaf_lists,
+                          (size_t)ctx->n_local_padded * 8u * RVPT_LIST_WORDS * sizeof(unsigned short)));
+        uint32_t G = ctx->frame_group;
+        while ((n_batch + G - 1u) / G > RVPT_MAX_GROUPS) G *= 2u;
+        uint32_t n = 0, at = 0;
+        for (; at < n_batch; at += G) p.group_start[n++] = (uint8_t)at;
+        p.group_start[n] = (uint8_t)n_batch;
+        p.n_groups = n;
+        p.leaf_lists = std::getenv("RVPT_B200_LIST_INLINE") ? nullptr : ctx->d_leaf_lists; /* developer knob */
     }
     p.samples = ctx->d_samples;
     p.sample_stride = ctx->n_local_padded * RVPT_TILE_PIXELS;

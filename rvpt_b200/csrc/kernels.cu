@@ -1224,8 +1224,37 @@ __device__ __forceinline__ void trace_listed(const SceneViewT<true>& sc, uint32_
     }
 }
 
+/* First phase of such a launch: every pixel block's leaf list, once, into p.leaf_lists (blocks are
+ * dealt statically; a grid barrier follows). */
+__device__ __forceinline__ void build_all_lists(const FrameParams& p, const SceneViewT<true>& sc)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t scratch = (uint32_t)sc.beam_scratch + (threadIdx.x >> 5) * 64u;
+    for (uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < p.n_chunks; c += n_warps)
+    {
+        uint32_t x, y;
+        slot_to_xy(p, c * 32u + lane, x, y);
+        __syncwarp(); /* the previous block's entries have been copied out */
+        uint32_t base, oct;
+        const uint32_t n_list = build_leaf_list(p, sc, x - (lane & 7u), y - (lane >> 3), scratch, base, oct);
+        unsigned short* rec = p.leaf_lists + (size_t)c * RVPT_LIST_WORDS;
+        if (n_list != RVPT_NO_LIST && lane < n_list)
+        {
+            unsigned short off;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(off) : "r"(scratch + 2u * lane));
+            rec[4u + lane] = off;
+        }
+        if (lane == 0)
+        {
+            rec[0] = n_list == RVPT_NO_LIST ? (unsigned short)RVPT_LIST_NONE : (unsigned short)n_list;
+            rec[1] = (unsigned short)oct;
+        }
+    }
+}
+
 /* primary_phase for batched launches of scenes with octant arrays and a pinhole camera
- * (p.frame_group > 0): a claimed unit is (pixel block, group of frame_group consecutive frames).
+ * (p.n_groups > 0): a claimed unit is (pixel block, group of consecutive frames of the batch).
  * What depends on the pixel block only — pixel coordinates, the RNG seed's hash, the leaf list —
  * is computed once per unit. */
 __device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const SceneViewT<true>& sc, bool sort)
@@ -1234,9 +1263,7 @@ __device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const S
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long traced = 0;
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t G = p.frame_group;
-    const uint32_t n_groups = (p.n_batch + G - 1u) / G;
-    const uint32_t n_units = p.n_chunks * n_groups;
+    const uint32_t n_units = p.n_chunks * p.n_groups;
     const uint32_t scratch = (uint32_t)sc.beam_scratch + (threadIdx.x >> 5) * 64u;
     const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
     uint32_t shard = gwarp % RVPT_CHUNK_SHARDS;
@@ -1255,15 +1282,30 @@ __device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const S
         slot_to_xy(p, slot, x, y);
         const bool inside = (x < p.W_eff) && (y < p.H_eff) && ((slot >> 8) * p.nranks + p.rank < p.n_tiles);
         const uint32_t seed = rv_wang_hash(x + y * p.W) + p.frame; /* util.glsl:35-36, + frame_in_batch below */
-        const uint32_t fi_end = min(g * G + G, p.n_batch);
+        const uint32_t fi_begin = p.group_start[g], fi_end = p.group_start[g + 1u];
         if (p.max_bounces > 0)
-            traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside)) * (fi_end - g * G);
+            traced += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, inside)) * (fi_end - fi_begin);
 
+        /* the block's leaf list: built by the launch's first phase (copied into this warp's
+         * shared-memory slots), or here */
         __syncwarp(); /* nobody still reads the previous unit's list */
-        uint32_t base, oct;
-        const uint32_t n_list = build_leaf_list(p, sc, x - (lane & 7u), y - (lane >> 3), scratch, base, oct);
+        uint32_t n_list, oct, base;
+        if (p.leaf_lists)
+        {
+            const unsigned short* rec = p.leaf_lists + (size_t)c * RVPT_LIST_WORDS;
+            /* written by this launch: not the read-only path */
+            const uint32_t n_rec = __ldcg(rec);
+            oct = __ldcg(rec + 1);
+            n_list = n_rec == RVPT_LIST_NONE ? RVPT_NO_LIST : n_rec;
+            base = (uint32_t)sc.oct_rel_nodes + oct * sc.oct_stride;
+            if (n_list != RVPT_NO_LIST && lane < n_list)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(scratch + 2u * lane), "h"(__ldcg(rec + 4u + lane)) : "memory");
+            __syncwarp();
+        }
+        else
+            n_list = build_leaf_list(p, sc, x - (lane & 7u), y - (lane >> 3), scratch, base, oct);
 
-        for (uint32_t fi = g * G; fi < fi_end; ++fi)
+        for (uint32_t fi = fi_begin; fi < fi_end; ++fi)
         {
             const uint32_t tag = slot | (fi << RVPT_BATCH_SLOT_BITS);
             bool alive = false;
@@ -1696,11 +1738,18 @@ __global__ void __launch_bounds__(kThreads, (kSmem ? RVPT_MIN_CTAS : RVPT_GLOBAL
      * setup_scene */
     const bool sort = p.bin_cap != 0u && ordered_bounce != 0u;
     bool listed = false;
-    if constexpr (kSmem && kRel && kOct && kBatch) listed = p.frame_group != 0u && sc.beam_scratch != 0u;
+    if constexpr (kSmem && kRel && kOct && kBatch) listed = p.n_groups != 0u && sc.beam_scratch != 0u;
     if constexpr (kSmem && kRel && kOct && kBatch)
     {
         if (listed)
+        {
+            if (p.leaf_lists)
+            {
+                build_all_lists(p, sc);
+                grid.sync();
+            }
             primary_phase_beam(p, sc, sort);
+        }
         else
             primary_phase<kSmem, kRel, kOct, kBatch>(p, sc, sort);
     }
