@@ -69,7 +69,8 @@ struct rvpt_b200_ctx
     bool scene_smem = false;
     bool scene_oct = false; /* direction-octant node copies fit next to the blob */
     bool scene_nested = false; /* every child box lies inside its parent's, all bounds finite (leaf lists) */
-    uint32_t frame_group = 8; /* frames per (pixel block, frame group) unit of a batched primary wave; 0: no leaf lists */
+    uint32_t frame_group = 16; /* most frames per (pixel block, frame group) unit of a batched primary wave; 0: no leaf lists */
+    bool frame_group_fixed = false; /* RVPT_B200_FRAME_GROUP: exactly that many */
     bool have_scene = false;
     /* integrator_Hart (render mode 10) marches against the caller's vertices, not the packed
      * records: the 64-byte triangles in the order the shader's buffer holds them (the caller's, or
@@ -844,7 +845,7 @@ extern "C" int rvpt_b200_create(rvpt_b200_ctx** out, int device, uint32_t width,
     if (const char* e = std::getenv("RVPT_B200_TAIL_RAYS_PER_WARP")) /* developer knob (tuning runs) */
         ctx->tail_rays_per_warp = (uint32_t)std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RVPT_B200_FRAME_GROUP")) /* developer knob (tuning runs); 0 = no leaf lists */
-        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
+        ctx->frame_group = (uint32_t)std::min(64, std::max(0, std::atoi(e))), ctx->frame_group_fixed = true;
     if (const char* e = std::getenv("RVPT_B200_QUEUE_BUDGET_MIB")) /* path-queue memory budget */
         ctx->queue_budget = (size_t)std::max(1, std::atoi(e)) << 20;
     ctx->device = device;
@@ -1134,6 +1135,14 @@ int render_launches(rvpt_b200_ctx* ctx, const rvpt_render_settings* rs, const fl
             CU(cudaMalloc(&ctx->d_leaf_lists,
                           (size_t)ctx->n_local_padded * 8u * RVPT_LIST_WORDS * sizeof(unsigned short)));
         uint32_t G = ctx->frame_group;
+        if (!ctx->frame_group_fixed)
+        {
+            /* same box, C2 on one GPU: groups of 4 / 8 / 16 / 32 frames 29.2 / 29.9 / 30.3 / 30.4
+             * Gsamples/s; one rank of eight (tools/timeline.py --nranks 8): 8-frame groups leave a
+             * 28 us tail. At least 12 units per resident warp. */
+            const uint64_t want = 12ull * (uint64_t)ctx->grid_frame * (rvpt::threads_per_cta() / 32);
+            while (G > 4u && (uint64_t)p.n_chunks * ((n_batch + G - 1u) / G) < want) G >>= 1;
+        }
         while ((n_batch + G - 1u) / G > RVPT_MAX_GROUPS) G *= 2u;
         uint32_t n = 0, at = 0;
         for (; at < n_batch; at += G) p.group_start[n++] = (uint8_t)at;

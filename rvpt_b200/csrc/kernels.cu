@@ -1085,10 +1085,11 @@ __device__ __forceinline__ uint32_t resolve_claim(uint32_t* ctr, uint32_t n_unit
 
 /* The primary rays of one 8x4 pixel block form a thin beam from the camera origin, the same beam
  * in every frame of a batch (only the jitter inside each pixel changes). build_leaf_list()
- * collects — once per (pixel block, group of frames) — the leaves whose boxes ANY ray of that beam
- * can enter, in the order of the beam's octant array, into 32 u16 entries of shared memory per
- * warp; the rays of the block then test exactly those leaf boxes, with the walk's own slab
- * arithmetic, instead of walking the tree.
+ * collects the leaves whose boxes ANY ray of that beam can enter, in the order of the beam's
+ * octant array, into 32 u16 entries of shared memory per warp — once per pixel block and launch
+ * (build_all_lists, the launch's first phase, keeps the lists in global memory); the rays of the
+ * block, in every frame of the batch, then test exactly those leaf boxes, with the walk's own
+ * slab arithmetic, instead of walking the tree.
  *
  * Why this is the walk's result bit for bit: a leaf box lies inside every ancestor's box (the
  * host checks it, SceneLayout::nested), subtraction and multiplication by one invdir are

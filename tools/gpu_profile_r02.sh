@@ -4,7 +4,7 @@
 # turns them into profiles/.
 mkdir -p gpurun_out
 TAG=${1:-r02}
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+[ -n "$SKIP_TESTS" ] || timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 600 python bench.py > gpurun_out/bench_${TAG}_n1.json 2> gpurun_out/bench_${TAG}_n1.err
 timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_${TAG}_reference.json 2>/dev/null
 timeout 300 python bench.py --pose pinned --no-cpu-baseline --no-c4 > gpurun_out/bench_${TAG}_pinned.json 2>/dev/null
