@@ -145,6 +145,7 @@ struct WaveGroups
  * wave-size forecast looks at.
  */
 #define RVPT_CHUNK_SHARDS 16u
+#define RVPT_QCOUNT_STRIDE 32u /* words between the sub-queue counters of a wave: one 128-byte line each */
 struct WaveCounters
 {
     /* primary phase work distribution: one counter per shard, 128 B apart so the
@@ -153,9 +154,12 @@ struct WaveCounters
     uint32_t work_ctr[64]; /* k_bounce (one launch per wave): the claimed eighth of wave b */
     /* k_frame's big bounce waves: sharded like chunk_ctr, wave b uses set b & 1 */
     uint32_t bounce_ctr[2][RVPT_CHUNK_SHARDS * 32u];
-    /* survivors pushed by bounce b (read by b+1) per sub-queue; a binned sub-queue's counter may
-     * run past bin_cap (the excess went to the overflow sub-queue): readers clamp it */
-    uint32_t qcount[64][RVPT_SORT_BINS + 1];
+    /* survivors pushed by bounce b (read by b+1) per sub-queue: [b][k] for sorted appends and the
+     * overflow sub-queue (k = RVPT_SORT_BINS), [b][(1 + k) * RVPT_QCOUNT_STRIDE] for unsorted appends
+     * spread over the binned sub-queues (a wave uses one of the two; readers add them). A binned
+     * sub-queue's counter may run past bin_cap (the excess went to the overflow sub-queue): readers
+     * clamp it */
+    uint32_t qcount[64][(RVPT_SORT_BINS + 1) * RVPT_QCOUNT_STRIDE];
 };
 struct FrameStats
 {

@@ -783,6 +783,26 @@ __device__ __forceinline__ void push_survivors(const FrameParams& p, const PathQ
             i = bin * p.bin_cap + my;
         }
     }
+    else if (p.bin_cap != 0u)
+    {
+        /* Unsorted, but not through ONE counter: a 64-frame launch of C2 appends 1.8 M times, and
+         * same-address atomics retire at one per ~1.5 SM cycles — 1.4 ms of a 2 ms primary wave, so
+         * the wave sat on the edge of that limit: whether it fell over it depended on the build and
+         * on where the counter happened to live (C2 rendered at 30.3 or at 25.3 Gsamples/s; ncu put
+         * 25 % of all stall samples on the shuffle that waits for the append's base index). The
+         * binned sub-queues are there anyway: warp w appends to sub-queue w % 8, through a counter
+         * of its own 128-byte line (the sorted path keeps its nine counters in ONE line: the up to
+         * eight atomics of a warp's push then travel as one request — spreading them cost the
+         * Cornell box 6 %). A wave is appended to either sorted or unsorted, never both. */
+        const uint32_t bin = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % RVPT_SORT_BINS;
+        const uint32_t first = (uint32_t)(__ffs(mask) - 1);
+        uint32_t base = 0;
+        if (lane == first) base = atomicAdd(&qcount[(1u + bin) * RVPT_QCOUNT_STRIDE], (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, first);
+        const uint32_t my = base + __popc(mask & ((1u << lane) - 1u));
+        spill = alive && my >= p.bin_cap;
+        i = bin * p.bin_cap + my;
+    }
     const uint32_t smask = __ballot_sync(0xFFFFFFFFu, spill);
     if (smask)
     {
@@ -813,7 +833,8 @@ __device__ __forceinline__ uint32_t prepare_wave(const FrameParams& p, WaveGroup
     constexpr uint32_t kQ = RVPT_SORT_BINS + 1u;
     for (uint32_t k = threadIdx.x; k < kQ; k += blockDim.x)
     {
-        const uint32_t c = *reinterpret_cast<const volatile uint32_t*>(&qcount[k]);
+        uint32_t c = *reinterpret_cast<const volatile uint32_t*>(&qcount[k]);
+        if (k < RVPT_SORT_BINS) c += *reinterpret_cast<const volatile uint32_t*>(&qcount[(1u + k) * RVPT_QCOUNT_STRIDE]);
         wg.cnt[k] = k < RVPT_SORT_BINS ? min(c, p.bin_cap) : c;
     }
     __syncthreads();
@@ -1265,7 +1286,10 @@ __device__ __forceinline__ void primary_phase_beam(const FrameParams& p, const S
     unsigned long long traced = 0;
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t n_units = p.n_chunks * p.n_groups;
-    const uint32_t scratch = (uint32_t)sc.beam_scratch + (threadIdx.x >> 5) * 64u;
+    uint32_t scratch = (uint32_t)sc.beam_scratch + (threadIdx.x >> 5) * 64u;
+    /* opaque to ptxas, which otherwise re-derives this address (shared window base, constant-bank
+     * loads, scene sizes: 14 uniform-datapath instructions) in every iteration of the list loop */
+    asm volatile("" : "+r"(scratch));
     const rv_f3 o = rv_make(p.cam[12], p.cam[13], p.cam[14]);
     uint32_t shard = gwarp % RVPT_CHUNK_SHARDS;
     uint32_t claim = 0;
