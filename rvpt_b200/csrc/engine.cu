@@ -80,6 +80,7 @@ struct rvpt_b200_ctx
     float4* d_raw_tris = nullptr;
     size_t raw_capacity = 0;   /* triangles d_raw_tris can hold */
     bool raw_valid = false;    /* d_raw_tris holds the current scene */
+    bool raw_source_ok = false; /* scene_inputs / raw_sorted are the arrays of the scene on the device (the last upload succeeded) */
 
     /* frame buffers (tile layout) */
     void* d_accum = nullptr;      /* own allocation */
@@ -968,6 +969,7 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
         }
         ctx->scene_blob_bytes = 0; /* invalid until this upload succeeds */
         ctx->raw_valid = false;
+        ctx->raw_source_ok = false;
         ctx->raw_sorted.clear();
         ctx->scene_inputs.resize(hdr + nb + tb + mb);
         std::memcpy(ctx->scene_inputs.data(), counts, hdr);
@@ -1004,7 +1006,9 @@ extern "C" int rvpt_b200_upload_scene(rvpt_b200_ctx* ctx, const rvpt_bvh_node* n
         ps.coincident_faces = has_coincident_faces(triangles, n_triangles);
     else
         ps.coincident_faces = true;
-    return upload_packed(ctx, ps);
+    rc = upload_packed(ctx, ps);
+    ctx->raw_source_ok = rc == 0;
+    return rc;
 }
 
 namespace
@@ -1014,6 +1018,9 @@ namespace
 int ensure_raw_triangles(rvpt_b200_ctx* ctx)
 {
     if (ctx->raw_valid) return 0;
+    if (!ctx->raw_source_ok)
+        return fail(ctx, RVPT_B200_ENOSCENE, "integrator_Hart needs the triangles of the scene on the device, and the last "
+                                             "upload_scene failed: upload the scene again");
     const rvpt_triangle* src = nullptr;
     size_t n = 0;
     if (!ctx->raw_sorted.empty())
